@@ -1,0 +1,93 @@
+"""ctypes binding of libbas_b200.so (include/bas_b200.h).
+
+There is no CPU fallback: if the library is missing the import fails with the build command, and
+every compute entry point needs a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libbas_b200.so')
+
+ABI_VERSION = 1
+N_DIRECTIONS = 187
+MAX_TERMS = 16
+AZ_PYFLOAT, AZ_F64, AZ_F32 = 0, 1, 2
+ERR_AZIM_ASSERT, ERR_VERT_ASSERT, ERR_NONFINITE = 1, 2, 4
+E_ARG, E_UNSUPPORTED, E_NO_DEVICE = -1, -2, -3
+RENDER_AUTO, RENDER_GENERIC, RENDER_TILED = 0, 1, 2
+
+
+class Term(C.Structure):
+    _fields_ = [('row_shift', C.c_int32), ('weight', C.c_float)]
+
+
+class Trace(C.Structure):
+    _fields_ = [('rows', C.c_int32 * 4), ('err', C.c_int32), ('pad', C.c_int32),
+                ('alpha_top', C.c_double), ('alpha_bot', C.c_double), ('a', C.c_double),
+                ('lo', (C.c_int64 * 6) * 2), ('hi', (C.c_int64 * 6) * 2)]
+
+
+TRACE_DTYPE = [('rows', '<i4', (4,)), ('err', '<i4'), ('pad', '<i4'), ('alpha_top', '<f8'),
+               ('alpha_bot', '<f8'), ('a', '<f8'), ('lo', '<i8', (2, 6)), ('hi', '<i8', (2, 6))]
+TERM_DTYPE = [('row_shift', '<i4'), ('weight', '<f4')]
+
+
+class BasError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            'libbas_b200.so is not built (%s).  Build it with `python -c "import __graft_entry__ as g; g.build()"` '
+            'or `make -C binaural-audio-synthesis_b200/csrc`.  There is no CPU fallback.' % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp, ll, i, dp = C.c_void_p, C.c_longlong, C.c_int, C.POINTER(C.c_double)
+    sigs = {
+        'bas_abi_version': ([], i),
+        'bas_last_error': ([C.c_char_p, C.c_size_t], i),
+        'bas_device_count': ([], i),
+        'bas_bank_to_polyphase': ([vp, i, i, i, vp, vp], i),
+        'bas_plan_build': ([vp, vp, i, i, vp, vp, vp, i, ll, vp, vp, vp, vp], i),
+        'bas_plan_build_host': ([vp, vp, i, i, vp, vp, vp, i, ll, vp, vp], i),
+        'bas_ring_lookup_host': ([C.c_double, C.c_double, i, C.POINTER(i), dp, C.POINTER(i)], i),
+        'bas_plan_ring_host': ([vp, vp, i, i, i, i, C.c_double, C.c_double, vp, vp, vp, vp], i),
+        'bas_ir_synth': ([vp, i, i, vp, ll, i, vp, ll, vp], i),
+        'bas_render': ([vp, ll, ll, i, ll, i, i, i, vp, ll, vp, ll, ll, vp, ll, i, vp, i, vp], i),
+        'bas_normalise': ([vp, ll, vp, vp], i),
+        'bas_peak': ([vp, ll, vp, vp], i),
+        'bas_probe_fma': ([i, i, i, i, vp, vp], i),
+    }
+    for name, (argtypes, restype) in sigs.items():
+        fn = getattr(lib, name)          # AttributeError here = header and library out of step
+        fn.argtypes = argtypes
+        fn.restype = restype
+    if lib.bas_abi_version() != ABI_VERSION:
+        raise ImportError('libbas_b200.so has ABI %d, expected %d: rebuild it' % (lib.bas_abi_version(), ABI_VERSION))
+    return lib, tuple(sigs)
+
+
+lib, EXPORTS = _load()
+
+
+def last_error() -> str:
+    buf = C.create_string_buffer(512)
+    lib.bas_last_error(buf, 512)
+    return buf.value.decode(errors='replace')
+
+
+def check(rc: int, what: str) -> None:
+    """Raise on a non-zero status from a launch-type entry point."""
+    if rc != 0:
+        raise BasError('%s failed (status %d): %s' % (what, rc, last_error()))
+
+
+def require_device():
+    """The product path has no CPU implementation: fail loudly without a CUDA device."""
+    import torch
+    if not torch.cuda.is_available() or lib.bas_device_count() < 1:
+        raise BasError('binaural-audio-synthesis_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
+    return torch

@@ -1,0 +1,143 @@
+// K1  plan_build: one fp64 thread per trajectory point.
+//
+// Replaces the scalar arithmetic of interpolate_2d (apply_hrtf.py:199-215, :244-252, :261-266,
+// :272-273), of delay_signal_float (apply_hrtf.py:149-151) and of
+// sphere.azim_to_interpolation_params (sphere.py:78-121).  The arithmetic itself lives in
+// plan_math.h and is also compiled for the host (bas_plan_build_host) from the same source.
+//
+// COMPILE THIS FILE WITH -fmad=false: a fused multiply-add would change floor()/ceil() inputs.
+#include <limits.h>
+#include <stdarg.h>
+
+#include "bas_internal.cuh"
+#include "plan_math.h"
+
+static_assert(sizeof(BasTerm) == sizeof(bas_term), "term layout");
+static_assert(sizeof(BasTrace) == sizeof(bas_trace), "trace layout");
+static_assert(BAS_MAX_TERMS == 16 && BAS_N_DIR == BAS_N_DIRECTIONS, "constants");
+
+// ---- thread-local error string (defined once, here) -----------------------------------------
+static thread_local char g_err[512] = "";
+
+void bas_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" int bas_last_error(char* buf, size_t len) {
+    if (!buf || len == 0) return BAS_E_ARG;
+    strncpy(buf, g_err, len - 1);
+    buf[len - 1] = 0;
+    return 0;
+}
+
+extern "C" int bas_abi_version(void) { return BAS_ABI_VERSION; }
+
+extern "C" int bas_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ---- device kernel ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+bas_plan_kernel(const double* __restrict__ diffs_l, const double* __restrict__ diffs_r, int U, long long L,
+                const double* __restrict__ elev, const double* __restrict__ azim,
+                const uint8_t* __restrict__ az_kind, int az_kind_all, long long n_points,
+                BasTerm* __restrict__ terms, BasTrace* __restrict__ trace, int* __restrict__ status) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_points) return;
+    const int kind = az_kind ? (int)az_kind[p] : az_kind_all;
+    BasTerm local[2 * BAS_MAX_TERMS];
+    const int err = bas_plan_point(diffs_l, diffs_r, U, L, elev[p], azim[p], kind, local, trace ? trace + p : nullptr);
+    // 2 x 16 x 8 B = 256 B per point, written as 16 x 16 B
+    int4* dst = reinterpret_cast<int4*>(terms + p * 2 * BAS_MAX_TERMS);
+    const int4* src = reinterpret_cast<const int4*>(local);
+#pragma unroll
+    for (int i = 0; i < BAS_MAX_TERMS; ++i) dst[i] = src[i];
+    if (err && status) {
+        atomicOr(status, err);
+        atomicMin(status + 1, (int)(p > INT_MAX ? INT_MAX : p));
+    }
+}
+
+extern "C" int bas_plan_build(const double* diffs_left_dev, const double* diffs_right_dev, int U, int L,
+                              const double* elev_dev, const double* azim_dev, const uint8_t* az_kind_dev,
+                              int az_kind_all, long long n_points, bas_term* terms_dev, bas_trace* trace_dev,
+                              int* status_dev, void* stream) {
+    BAS_CHECK_ARG(diffs_left_dev && diffs_right_dev && elev_dev && azim_dev && terms_dev, "null pointer");
+    BAS_CHECK_ARG(U >= 1 && L >= U && L % U == 0 && L < (1 << 20), "need 1 <= U, U | L, L < 2^20");
+    BAS_CHECK_ARG(az_kind_all >= 0 && az_kind_all <= 2, "az_kind_all");
+    BAS_CHECK_ARG(n_points >= 0, "n_points");
+    if (n_points == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (status_dev) {
+        // {0, 0x7f7f7f7f}: memsets keep the call capturable in a CUDA graph
+        BAS_CUDA(cudaMemsetAsync(status_dev, 0, sizeof(int), st));
+        BAS_CUDA(cudaMemsetAsync(status_dev + 1, 0x7f, sizeof(int), st));
+    }
+    const int threads = 128;
+    const long long blocks = bas_ceil_div(n_points, threads);
+    BAS_CHECK_ARG(blocks < 0x7fffffffLL, "too many points for one launch");
+    bas_plan_kernel<<<(unsigned)blocks, threads, 0, st>>>(
+        diffs_left_dev, diffs_right_dev, U, (long long)L, elev_dev, azim_dev, az_kind_dev, az_kind_all, n_points,
+        reinterpret_cast<BasTerm*>(terms_dev), reinterpret_cast<BasTrace*>(trace_dev), status_dev);
+    BAS_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- host twins (same plan_math.h) -----------------------------------------------------------
+extern "C" int bas_plan_build_host(const double* diffs_left, const double* diffs_right, int U, int L,
+                                   const double* elev, const double* azim, const uint8_t* az_kind,
+                                   int az_kind_all, long long n_points, bas_term* terms, bas_trace* trace) {
+    BAS_CHECK_ARG(diffs_left && diffs_right && elev && azim && terms, "null pointer");
+    BAS_CHECK_ARG(U >= 1 && L >= U && L % U == 0 && L < (1 << 20), "need 1 <= U, U | L, L < 2^20");
+    int err = 0;
+    for (long long p = 0; p < n_points; ++p) {
+        const int kind = az_kind ? (int)az_kind[p] : az_kind_all;
+        err |= bas_plan_point(diffs_left, diffs_right, U, L, elev[p], azim[p], kind,
+                              reinterpret_cast<BasTerm*>(terms) + p * 2 * BAS_MAX_TERMS,
+                              trace ? reinterpret_cast<BasTrace*>(trace) + p : nullptr);
+    }
+    return err;
+}
+
+extern "C" int bas_ring_lookup_host(double ring_elev, double azim, int az_kind, int* before, double* alpha, int* after) {
+    BAS_CHECK_ARG(before && alpha && after, "null pointer");
+    BAS_CHECK_ARG(az_kind >= 0 && az_kind <= 2, "az_kind");
+    // sphere.py:88 clips the elevation, :90-98 match it against the table with 1e-5 tolerance
+    double e = ring_elev;
+    if (e < bas_ring_elev(0)) e = bas_ring_elev(0);
+    if (e > bas_ring_elev(BAS_N_RING - 1)) e = bas_ring_elev(BAS_N_RING - 1);
+    int r = -1;
+    for (int k = 0; k < BAS_N_RING; ++k)
+        if (fabs(bas_ring_elev(k) - e) < 0.00001) r = k;
+    // the azimuth assertion (sphere.py:87) precedes the ring check (:100-101)
+    BasRing rg;
+    const int err = bas_ring_lookup(r < 0 ? 0 : r, azim, az_kind, &rg);
+    if (err) return err;
+    if (r < 0) {
+        bas_set_error("bas_ring_lookup_host: elevation %.9g is not a grid ring", ring_elev);
+        return BAS_E_ARG;
+    }
+    *before = rg.before; *alpha = rg.alpha; *after = rg.after;
+    return 0;
+}
+
+extern "C" int bas_plan_ring_host(const double* diffs_left, const double* diffs_right, int U, int L, int before,
+                                  int after, double alpha, double one_minus_alpha, bas_term* terms,
+                                  double* delays, int64_t* lo, int64_t* hi) {
+    BAS_CHECK_ARG(diffs_left && diffs_right && terms && delays, "null pointer");
+    BAS_CHECK_ARG(before >= 0 && before < BAS_N_DIR && after >= 0 && after < BAS_N_DIR, "row index");
+    BAS_CHECK_ARG(U >= 1 && L >= U && L % U == 0 && L < (1 << 20), "need 1 <= U, U | L, L < 2^20");
+    int err = 0;
+    for (int e = 0; e < 2; ++e) {
+        long long l2[2], h2[2];
+        err |= bas_plan_ring_ear(e ? diffs_right : diffs_left, U, L, before, after, alpha, one_minus_alpha,
+                                 reinterpret_cast<BasTerm*>(terms) + e * BAS_MAX_TERMS, delays + e, l2, h2);
+        if (lo && hi) { lo[2 * e] = l2[0]; lo[2 * e + 1] = l2[1]; hi[2 * e] = h2[0]; hi[2 * e + 1] = h2[1]; }
+    }
+    return err;
+}
