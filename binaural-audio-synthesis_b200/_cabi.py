@@ -18,6 +18,7 @@ AZ_PYFLOAT, AZ_F64, AZ_F32 = 0, 1, 2
 ERR_AZIM_ASSERT, ERR_VERT_ASSERT, ERR_NONFINITE = 1, 2, 4
 E_ARG, E_UNSUPPORTED, E_NO_DEVICE = -1, -2, -3
 RENDER_AUTO, RENDER_GENERIC, RENDER_TILED = 0, 1, 2
+IR_UPSAMPLED, IR_PLANAR, IR_ROWS = 0, 1, 2
 
 
 class Term(C.Structure):
@@ -56,7 +57,8 @@ def _load():
         'bas_ring_lookup_host': ([C.c_double, C.c_double, i, C.POINTER(i), dp, C.POINTER(i)], i),
         'bas_plan_ring_host': ([vp, vp, i, i, i, i, C.c_double, C.c_double, vp, vp, vp, vp], i),
         'bas_ir_synth': ([vp, i, i, vp, ll, i, vp, ll, vp], i),
-        'bas_render': ([vp, ll, ll, i, ll, i, i, i, vp, ll, vp, ll, ll, vp, ll, i, vp, i, vp], i),
+        'bas_filter_row_pitch': ([i], i),
+        'bas_render': ([vp, ll, ll, i, ll, i, i, i, vp, vp, ll, ll, vp, ll, i, vp, i, vp], i),
         'bas_normalise': ([vp, ll, vp, vp], i),
         'bas_peak': ([vp, ll, vp, vp], i),
         'bas_probe_fma': ([i, i, i, i, vp, vp], i),

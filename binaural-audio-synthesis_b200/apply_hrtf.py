@@ -188,7 +188,8 @@ def delay_compensated_interpolation_with_delaydiff(irs_and_delaydiffs, before: i
     terms_dev = torch.from_numpy(terms.view(np.uint8).reshape(-1)).to(dev.device)
     out = torch.empty((1, 2, width), dtype=torch.float32, device=dev.device)
     _cabi.check(lib.bas_ir_synth(dev.bank_pp.data_ptr(), dev.upsampling, dev.taps, terms_dev.data_ptr(), 1,
-                                 0 if return_upsampled else 1, out.data_ptr(), width, _stream(torch)), 'bas_ir_synth')
+                                 _cabi.IR_UPSAMPLED if return_upsampled else _cabi.IR_PLANAR, out.data_ptr(), width,
+                                 _stream(torch)), 'bas_ir_synth')
     irs = out[0].cpu().numpy().astype(np.float64)
     return (delays[0], delays[1], irs)
 
@@ -225,7 +226,7 @@ def interpolate_2d_batch(irs_and_delaydiffs, elev, azim, az_kind=_cabi.AZ_F64, r
     n = elev_d.numel()
     if azim_d.numel() != n:
         raise ValueError('elev and azim must have the same number of points')
-    filt, status, trace = _plan_and_synth(torch, dev, elev_d, azim_d, az_kind, n, dev.taps, return_trace)
+    filt, status, trace = _plan_and_synth(torch, dev, elev_d, azim_d, az_kind, n, _cabi.IR_PLANAR, return_trace)
     if check:
         err, where = (int(v) for v in status.cpu())
         if err:
@@ -235,9 +236,10 @@ def interpolate_2d_batch(irs_and_delaydiffs, elev, azim, az_kind=_cabi.AZ_F64, r
     return filt
 
 
-def _plan_and_synth(torch, dev, elev_d, azim_d, az_kind, n, filt_stride, want_trace=False):
-    """plan_build + ir_synth for n directions already on the device; returns (filters
-    (n, 2, filt_stride) fp32, status int32[2], trace bytes or None), all asynchronous."""
+def _plan_and_synth(torch, dev, elev_d, azim_d, az_kind, n, mode, want_trace=False):
+    """plan_build + ir_synth for n directions already on the device; returns (filters, status
+    int32[2], trace bytes or None), all asynchronous.  mode IR_PLANAR: filters (n, 2, K);
+    IR_ROWS: (n, pitch, 2) filter rows for bas_render."""
     stream = _stream(torch)
     if np.isscalar(az_kind):
         kinds_ptr, kind_all, kinds_d = None, int(az_kind), None
@@ -254,9 +256,12 @@ def _plan_and_synth(torch, dev, elev_d, azim_d, az_kind, n, filt_stride, want_tr
                                    elev_d.data_ptr(), azim_d.data_ptr(), kinds_ptr, kind_all, n, terms.data_ptr(),
                                    trace.data_ptr() if want_trace else None, status.data_ptr(), stream),
                 'bas_plan_build')
-    filt = torch.empty((n, 2, filt_stride), dtype=torch.float32, device=dev.device)
-    _cabi.check(lib.bas_ir_synth(dev.bank_pp.data_ptr(), dev.upsampling, dev.taps, terms.data_ptr(), n, 1,
-                                 filt.data_ptr(), filt_stride, stream), 'bas_ir_synth')
+    if mode == _cabi.IR_ROWS:
+        filt = torch.empty((n, lib.bas_filter_row_pitch(dev.taps), 2), dtype=torch.float32, device=dev.device)
+    else:
+        filt = torch.empty((n, 2, dev.taps), dtype=torch.float32, device=dev.device)
+    _cabi.check(lib.bas_ir_synth(dev.bank_pp.data_ptr(), dev.upsampling, dev.taps, terms.data_ptr(), n, mode,
+                                 filt.data_ptr(), dev.taps, stream), 'bas_ir_synth')
     return filt, status, trace
 
 
@@ -269,8 +274,8 @@ def interpolate_2d(irs_and_delaydiffs, elev, azim):
     _raise_plan_error(int(trace['err'][0]))
     terms_dev = torch.from_numpy(terms.view(np.uint8).reshape(-1)).to(dev.device)
     out = torch.empty((1, 2, dev.taps), dtype=torch.float32, device=dev.device)
-    _cabi.check(lib.bas_ir_synth(dev.bank_pp.data_ptr(), dev.upsampling, dev.taps, terms_dev.data_ptr(), 1, 1,
-                                 out.data_ptr(), dev.taps, _stream(torch)), 'bas_ir_synth')
+    _cabi.check(lib.bas_ir_synth(dev.bank_pp.data_ptr(), dev.upsampling, dev.taps, terms_dev.data_ptr(), 1,
+                                 _cabi.IR_PLANAR, out.data_ptr(), dev.taps, _stream(torch)), 'bas_ir_synth')
     return out[0].cpu().numpy().astype(np.float64)
 
 
@@ -371,8 +376,7 @@ def render_sources(signals, chunksize: int, subchunksize: int, elev_azim_functio
     if elev_d.numel() != n_src * n_pts or azim_d.numel() != n_src * n_pts:
         raise ValueError('trajectories must give %d directions per source' % n_pts)
 
-    filt_stride = _round_up(k, 4)
-    filt, status, _ = _plan_and_synth(torch, dev, elev_d, azim_d, kinds, n_src * n_pts, filt_stride)
+    filt, status, _ = _plan_and_synth(torch, dev, elev_d, azim_d, kinds, n_src * n_pts, _cabi.IR_ROWS)
     p0, p1 = (0, n_out) if time_range is None else (int(time_range[0]), int(time_range[1]))
     if not 0 <= p0 <= p1 <= n_out:
         raise ValueError('time_range outside [0, %d]' % n_out)
@@ -384,7 +388,7 @@ def render_sources(signals, chunksize: int, subchunksize: int, elev_azim_functio
 
     def launch(gains):
         _cabi.check(lib.bas_render(x.data_ptr(), n_in, n_in, n_src, n_in, chunksize, subchunksize, k,
-                                   filt.data_ptr(), filt_stride, gains.data_ptr() if gains is not None else None,
+                                   filt.data_ptr(), gains.data_ptr() if gains is not None else None,
                                    p0, count, out.data_ptr(), stride, 1 if mix else 0, peaks.data_ptr(), variant,
                                    stream), 'bas_render')
 

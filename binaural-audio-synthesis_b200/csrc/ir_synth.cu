@@ -67,6 +67,54 @@ bas_ir_synth_kernel(const float* __restrict__ bank_pp, int U, int K, const BasTe
     }
 }
 
+// filter-row layout for the renderer: one CTA per point, both ears per thread, out[point][m][ear]
+// with taps K..pitch-1 zeroed (bas_filter_row_pitch).  Term tables of both ears are compacted first.
+__global__ void __launch_bounds__(kThreads)
+bas_ir_synth_rows_kernel(const float* __restrict__ bank_pp, int U, int K, int pitch,
+                         const BasTermDev* __restrict__ terms, float2* __restrict__ out) {
+    const long long point = blockIdx.x;
+    const int L = U * K;
+    __shared__ int s_base[2][kMaxTerms];
+    __shared__ int s_adv[2][kMaxTerms];
+    __shared__ float s_w[2][kMaxTerms];
+    __shared__ int s_n[2];
+    if (threadIdx.x < 64) {
+        const int ear = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        BasTermDev t; t.row_shift = 0; t.weight = 0.f;
+        if (lane < kMaxTerms) t = terms[(point * 2 + ear) * kMaxTerms + lane];
+        const bool live = t.weight != 0.f;
+        const unsigned mask = __ballot_sync(0xffffffffu, live);
+        if (live) {
+            const int slot = __popc(mask & ((1u << lane) - 1u));
+            const int row = t.row_shift >> 20, shift = t.row_shift & 0xFFFFF;
+            const int ph = (U - shift % U) % U;
+            s_base[ear][slot] = (ear * BAS_N_DIRECTIONS + row) * L + ph * K;
+            s_adv[ear][slot] = (shift + ph) / U;
+            s_w[ear][slot] = t.weight;
+        }
+        if (lane == 0) s_n[ear] = __popc(mask);
+    }
+    __syncthreads();
+    const int n_l = s_n[0], n_r = s_n[1];
+    float2* dst = out + point * pitch;
+    for (int m = threadIdx.x; m < pitch; m += kThreads) {
+        float acc_l = 0.f, acc_r = 0.f;
+        if (m < K) {
+            for (int t = 0; t < n_l; ++t) {
+                int j = m - s_adv[0][t];
+                j += (j < 0) ? K : 0;
+                acc_l = fmaf(s_w[0][t], __ldg(bank_pp + s_base[0][t] + j), acc_l);
+            }
+            for (int t = 0; t < n_r; ++t) {
+                int j = m - s_adv[1][t];
+                j += (j < 0) ? K : 0;
+                acc_r = fmaf(s_w[1][t], __ldg(bank_pp + s_base[1][t] + j), acc_r);
+            }
+        }
+        dst[m] = make_float2(acc_l, acc_r);
+    }
+}
+
 // return_upsampled=True: all L samples (apply_hrtf.py:97-99), used only by the ring entry point
 __global__ void __launch_bounds__(kThreads)
 bas_ir_synth_full_kernel(const float* __restrict__ bank_pp, int U, int K, const BasTermDev* __restrict__ terms,
@@ -94,20 +142,28 @@ bas_ir_synth_full_kernel(const float* __restrict__ bank_pp, int U, int K, const 
 
 }  // namespace
 
+extern "C" int bas_filter_row_pitch(int K) { return K < 1 ? BAS_E_ARG : (K + 31) / 32 * 32 + 2; }
+
 extern "C" int bas_ir_synth(const float* bank_pp_dev, int U, int K, const bas_term* terms_dev, long long n_points,
-                            int decimate, float* out_dev, long long out_stride, void* stream) {
+                            int mode, float* out_dev, long long out_stride, void* stream) {
     BAS_CHECK_ARG(bank_pp_dev && terms_dev && out_dev, "null pointer");
     BAS_CHECK_ARG(U >= 1 && K >= 1 && (long long)U * K < (1 << 20), "need U, K >= 1 and U*K < 2^20");
     BAS_CHECK_ARG(n_points >= 0 && n_points < 0x7fffffffLL, "n_points");
-    BAS_CHECK_ARG(out_stride >= (decimate ? K : U * K) && out_stride < 0x7fffffffLL, "out_stride too small");
+    BAS_CHECK_ARG(mode == BAS_IR_UPSAMPLED || mode == BAS_IR_PLANAR || mode == BAS_IR_ROWS, "mode");
+    if (mode != BAS_IR_ROWS)
+        BAS_CHECK_ARG(out_stride >= (mode == BAS_IR_PLANAR ? K : U * K) && out_stride < 0x7fffffffLL, "out_stride too small");
     if (n_points == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     const BasTermDev* terms = reinterpret_cast<const BasTermDev*>(terms_dev);
-    if (decimate) {
+    if (mode == BAS_IR_ROWS) {
+        BAS_CHECK_ARG((reinterpret_cast<uintptr_t>(out_dev) & 15) == 0, "filter rows must be 16-byte aligned");
+        bas_ir_synth_rows_kernel<<<(unsigned)n_points, kThreads, 0, st>>>(bank_pp_dev, U, K, bas_filter_row_pitch(K), terms,
+                                                                         reinterpret_cast<float2*>(out_dev));
+    } else if (mode == BAS_IR_PLANAR) {
         dim3 grid((unsigned)n_points, 2);
         bas_ir_synth_kernel<<<grid, kThreads, 0, st>>>(bank_pp_dev, U, K, terms, out_dev, out_stride);
     } else {
-        BAS_CHECK_ARG(n_points <= 65535, "n_points <= 65535 when decimate=0");
+        BAS_CHECK_ARG(n_points <= 65535, "n_points <= 65535 when mode is BAS_IR_UPSAMPLED");
         dim3 grid((unsigned)bas_ceil_div(out_stride, kThreads), (unsigned)n_points, 2);
         bas_ir_synth_full_kernel<<<grid, kThreads, 0, st>>>(bank_pp_dev, U, K, terms, out_dev, out_stride);
     }

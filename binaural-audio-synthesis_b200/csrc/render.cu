@@ -11,19 +11,30 @@
 // no overlap-add traffic, bit-reproducible.
 //
 // bas_render_generic_kernel   any (C, S, K): one thread per output sample.  Reference-shaped, slow.
-// bas_render_tiled_kernel     S == 32: register-tiled FP32 kernel on the packed-FMA pipe.
+// bas_render_tiled_kernel     S == 32: persistent, TMA-fed, register-tiled kernel on the packed
+//                             FP32 FMA pipe.
 //
-// Tiled kernel, per warp: lane l owns the 32 consecutive outputs of block b = b0 + l (both ears: 32
-// fma.rn.f32x2 accumulators {L,R}).  Output block b draws on input subchunks q = b - d, d = 0..D:
-//     out[32b + r] += x[32q + m] * h_q[32d + r - m]        r, m = 0..31
-// All lanes of the warp sit at the same (d, m) so subchunk boundaries are warp-uniform; each lane
-// keeps a 32-entry ring of taps h_q[32d + r - m] in registers and slides it by one tap per m.  Taps
-// are blended on the fly from shared memory rows that hold {H_i, H_{i+1} - H_i} for both ears as one
-// 16-byte entry per tap (one LDS.128 + one packed FMA per new tap); lanes in the same chunk read the
-// same entry (broadcast), lanes in different chunks hit different banks (odd row stride).  The input
-// tile sits in shared memory with a 128-byte XOR swizzle so the stride-32 lane pattern is conflict
-// free.  FMA : LDS.128 ratio is 1087 : 71 per 32x32 block, so the kernel is bound by the FP32 pipe,
-// as SURVEY.md 8(d) predicts (arithmetic intensity ~95-190 flop per HBM byte).
+// Tiled kernel
+//   work     A CTA of TW warps owns tiles of TW*1024 consecutive outputs (one 1024-output stripe
+//            per warp) and walks over its tiles persistently (grid = resident CTAs).
+//   staging  For every (tile, source) item one warp issues cp.async.bulk (TMA, 1-D) copies into a
+//            two-stage shared-memory ring guarded by full/empty mbarriers: the input samples as
+//            128-byte rows on a 144-byte pitch (conflict-free for the lane-per-row reads below) and
+//            the boundary-filter rows of the chunks the tile touches as ONE contiguous copy (rows
+//            come from ir_synth already interleaved {L,R} and zero padded).  The copy of item j+1
+//            overlaps the arithmetic of item j; there is no __syncthreads in the kernel.
+//   math     Lane l of a warp owns the 32 consecutive outputs of block b = b0 + l for both ears: 32
+//            fma.rn.f32x2 accumulators {L,R}.  Output block b draws on input subchunks q = b - d:
+//                out[32b + r] += x[32q + m] * h_q[32d + r - m]          r, m = 0..31
+//            All lanes sit at the same (d, m), so subchunk boundaries are warp-uniform; each lane
+//            keeps a 32-entry ring of blended taps in registers and slides it one tap per m.  The
+//            half-empty first (d = 0, r >= m) and last (d = D, r < m) blocks are folded into ONE
+//            32x32 block whose ring is initialised from the d = 0 filter and refilled from the
+//            d = D filter, so a tile costs exactly ceil(K/32) blocks of 1024 packed FMAs plus 126
+//            blend operations each (89 % useful at K = 256, 94 % at K = 512).
+//   taps     Blended on the fly: w = H_i + alpha (H_{i+1} - H_i) from two LDS.128 (two taps each);
+//            lanes in the same chunk read the same address (broadcast), other chunks other banks.
+//   epilogue Direct 16-byte global stores from registers, peak by warp reduction + one atomicMax.
 #include "bas_internal.cuh"
 
 namespace {
@@ -32,12 +43,15 @@ struct RenderParams {
     const float* x; long long x_stride; long long n_valid;
     int n_src; long long n_in;
     int C, S, K;
-    const float* filt; long long filt_stride; long long filt_src_stride;   // floats between sources
+    const float2* filt;            // [n_src][n_in/C + 1][pitch] {L, R}
+    int pitch;                     // taps per filter row
+    long long filt_src_stride;     // float2 entries between sources
     const float* gains;
     long long p_begin, p_end;      // rendered output range [p_begin, p_end)
     float* out; long long out_stride;
     int mix;
     float* peaks;
+    long long tiles;               // tiled kernel: tiles per source
 };
 
 __device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
@@ -65,7 +79,7 @@ bas_render_generic_kernel(RenderParams prm) {
         float acc_l = 0.f, acc_r = 0.f;
         if (live) {
             const float* x = prm.x + (long long)s * prm.x_stride;
-            const float* f = prm.filt + (long long)s * prm.filt_src_stride;
+            const float2* f = prm.filt + (long long)s * prm.filt_src_stride;
             for (int k = 0; k < prm.K; ++k) {
                 const long long n = p - k;
                 if (n < 0) break;
@@ -73,13 +87,11 @@ bas_render_generic_kernel(RenderParams prm) {
                 const long long chunk = n / prm.C;
                 const int j = (int)(n - chunk * prm.C) / prm.S * prm.S;          // apply_hrtf.py:438
                 const float alpha = (float)j / (float)prm.C;                     // :442
-                const float* h0 = f + chunk * 2 * prm.filt_stride;
-                const float* h1 = h0 + 2 * prm.filt_stride;
+                const float2 h0 = f[chunk * prm.pitch + k];
+                const float2 h1 = f[(chunk + 1) * prm.pitch + k];
                 const float xv = x[n];
-                const float hl = (1.f - alpha) * h0[k] + alpha * h1[k];          // :443
-                const float hr = (1.f - alpha) * h0[prm.filt_stride + k] + alpha * h1[prm.filt_stride + k];
-                acc_l = fmaf(xv, hl, acc_l);
-                acc_r = fmaf(xv, hr, acc_r);
+                acc_l = fmaf(xv, (1.f - alpha) * h0.x + alpha * h1.x, acc_l);    // :443, :445
+                acc_r = fmaf(xv, (1.f - alpha) * h0.y + alpha * h1.y, acc_r);    // :443, :446
             }
         }
         if (prm.peaks) {
@@ -103,7 +115,7 @@ bas_render_generic_kernel(RenderParams prm) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// tiled kernel
+// tiled kernel: PTX helpers
 // ------------------------------------------------------------------------------------------------
 typedef unsigned long long u64;
 
@@ -115,8 +127,7 @@ __device__ __forceinline__ u64 pack2(float lo, float hi) {
 __device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) {
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
 }
-// d = a * b + d on both halves (FFMA2 on sm_100)
-__device__ __forceinline__ void fma2_acc(u64& d, u64 a, u64 b) {
+__device__ __forceinline__ void fma2_acc(u64& d, u64 a, u64 b) {          // d += a * b  (FFMA2)
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
 }
 __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
@@ -124,248 +135,326 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
     return d;
 }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+    u64 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(void* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(void* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(void* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (UBLKCP in SASS)
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, void* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
 constexpr int kBlk = 32;                 // outputs per lane = subchunk size of the tiled kernel
-constexpr int kWarpTile = 32 * kBlk;     // 1024 outputs per tile-warp
-constexpr int kStagePitch = kBlk + 1;    // staging row pitch (floats): conflict-free for lane-private rows
+constexpr int kWarpTile = 32 * kBlk;     // 1024 outputs per warp
+constexpr int kXPitch = 36;              // floats per staged input row (32 samples + 16 bytes)
+constexpr int kStages = 2;
 
 // geometry shared by host and device
 struct TileGeom {
-    int D;              // last tap block: d = 0..D
-    int row_len;        // 16-byte entries per filter row (odd)
-    int x_rows;         // 32-sample rows of the input tile
-    int max_rows;       // filter rows (chunks) a CTA can need
+    int D;              // tap blocks per tile: ceil(K / 32)
+    int x_rows;         // 32-sample input rows of a tile
+    int f_rows;         // filter rows staged per tile (chunks touched + 1)
+    unsigned x_bytes, f_bytes, stage_bytes;
 };
 
-__host__ __device__ inline TileGeom tile_geom(int K, int C, int TW) {
+__host__ __device__ inline TileGeom tile_geom(int K, int C, int pitch, int TW) {
     TileGeom g;
-    g.D = (K + kBlk - 2) / kBlk;
-    g.row_len = kBlk * (g.D + 2) + 1;
+    g.D = (K + kBlk - 1) / kBlk;
     g.x_rows = TW * 32 + g.D;
-    g.max_rows = (g.x_rows * kBlk + C - 1) / C + 1;
+    g.f_rows = (g.x_rows * kBlk + C - 1) / C + 2;
+    g.x_bytes = (unsigned)g.x_rows * kXPitch * 4;
+    g.f_bytes = (unsigned)g.f_rows * pitch * 8;
+    g.stage_bytes = g.x_bytes + g.f_bytes;
     return g;
 }
+constexpr size_t kBarBytes = 64;         // 2 x full + 2 x empty mbarriers, padded
 
-// Shared memory: [ area A: filter rows | input tile ]  [ mix tile (only when mixing) ].
-// With one source per CTA the output staging tile aliases area A; when mixing, the per-source
-// scratch of the tap splits aliases area A and the running mix has its own tile behind it.
-__host__ __device__ inline size_t tile_stage_bytes(int TW) { return (size_t)2 * TW * 32 * kStagePitch * 4; }
-__host__ __device__ inline size_t tile_area_a_bytes(const TileGeom& g, int TW) {
-    const size_t rows_xs = (size_t)g.max_rows * g.row_len * 16 + (size_t)g.x_rows * kBlk * 4;
-    const size_t stage = tile_stage_bytes(TW);
-    return rows_xs > stage ? rows_xs : stage;
-}
-inline size_t tile_smem_bytes(const TileGeom& g, int TW, bool mix) {
-    return tile_area_a_bytes(g, TW) + (mix ? tile_stage_bytes(TW) : 0);
-}
-
-// One 32x32 block of (input sample m) x (output r) products for both ears.
-//   acc[r] += {x[m], x[m]} * w[(r - m) & 31],   w slot (j & 31) holds tap 32d + j for j = r - m
-// rowp points at tap 32d of the lane's filter row (16-byte entries {H_L, H_R, D_L, D_R});
-// xrow points at the lane's swizzled 128-byte input row; swz = row & 7.
-__device__ __forceinline__ void block_32x32(u64 (&acc)[kBlk], const ulonglong2* __restrict__ rowp, u64 alpha2,
-                                            const float4* __restrict__ xrow, int swz) {
+// One 32x32 block: acc[r] += x_sel[m] * w[(r - m) & 31] for both ears, where ring slot j holds
+//   tap (base_a + j)        of the blend of rows (ra, ra + pitch)   for j = r - m >= 0   (x from xa)
+//   tap (base_b + j - 32)   of the blend of rows (rb, rb + pitch)   for j - 32 = r - m < 0 (x from xb)
+// ra/rb point at tap base_a / base_b of the lane's filter row (float2 {L,R} entries, 16-byte aligned).
+// For a full block (a, b) are the same filter and base_b = base_a; for the folded first/last block
+// a is the d = 0 filter (base 0) and b the d = D filter (base 32 D).
+__device__ __forceinline__ void block_32x32(u64 (&acc)[kBlk], const float2* __restrict__ ra, u64 alpha_a,
+                                            const float2* __restrict__ rb, u64 alpha_b, int pitch,
+                                            const float* __restrict__ xa, const float* __restrict__ xb) {
     u64 w[kBlk];
 #pragma unroll
-    for (int j = 0; j < kBlk; ++j) {
-        const ulonglong2 hd = rowp[j];
-        w[j] = fma2(alpha2, hd.y, hd.x);           // H + alpha * (H_next - H)   (apply_hrtf.py:443)
+    for (int j = 0; j < kBlk; j += 2) {
+        const ulonglong2 h0 = *reinterpret_cast<const ulonglong2*>(ra + j);
+        const ulonglong2 h1 = *reinterpret_cast<const ulonglong2*>(ra + pitch + j);
+        w[j] = fma2(alpha_a, sub2(h1.x, h0.x), h0.x);          // H_i + alpha (H_{i+1} - H_i)   apply_hrtf.py:443
+        w[j + 1] = fma2(alpha_a, sub2(h1.y, h0.y), h0.y);
     }
+    u64 pending = 0ull;
 #pragma unroll
     for (int m4 = 0; m4 < kBlk / 4; ++m4) {
-        const float4 xv = xrow[m4 ^ swz];
-        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+        const float4 xav = *reinterpret_cast<const float4*>(xa + 4 * m4);
+        const float4 xbv = *reinterpret_cast<const float4*>(xb + 4 * m4);
+        const float xas[4] = {xav.x, xav.y, xav.z, xav.w};
+        const float xbs[4] = {xbv.x, xbv.y, xbv.z, xbv.w};
 #pragma unroll
         for (int mm = 0; mm < 4; ++mm) {
             const int m = m4 * 4 + mm;
             if (m > 0) {
-                const ulonglong2 hd = rowp[-m];
-                w[(kBlk - m) & 31] = fma2(alpha2, hd.y, hd.x);
+                if (m & 1) {          // taps (base_b - m - 1, base_b - m) in one 16-byte load
+                    const ulonglong2 h0 = *reinterpret_cast<const ulonglong2*>(rb - m - 1);
+                    const ulonglong2 h1 = *reinterpret_cast<const ulonglong2*>(rb + pitch - m - 1);
+                    w[(kBlk - m) & 31] = fma2(alpha_b, sub2(h1.y, h0.y), h0.y);
+                    pending = fma2(alpha_b, sub2(h1.x, h0.x), h0.x);
+                } else {
+                    w[(kBlk - m) & 31] = pending;
+                }
             }
-            const u64 xx = pack2(xs[mm], xs[mm]);
+            const u64 xxa = pack2(xas[mm], xas[mm]);
+            const u64 xxb = pack2(xbs[mm], xbs[mm]);
 #pragma unroll
-            for (int r = 0; r < kBlk; ++r) fma2_acc(acc[r], xx, w[(r - m) & 31]);
+            for (int r = 0; r < kBlk; ++r) fma2_acc(acc[r], r >= m ? xxa : xxb, w[(r - m) & 31]);
         }
     }
 }
 
-template <int TW, int TS>
-__global__ void __launch_bounds__(TW * TS * 32)
+template <int TW, bool MIX>
+__global__ void __launch_bounds__(TW * 32, 1)
 bas_render_tiled_kernel(RenderParams prm) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const TileGeom g = tile_geom(prm.K, prm.C, TW);
-    float4* rows = reinterpret_cast<float4*>(smem);
-    float4* xs = rows + (size_t)g.max_rows * g.row_len;
-    float* stage = reinterpret_cast<float*>(prm.mix ? smem + tile_area_a_bytes(g, TW) : smem);
+    extern __shared__ __align__(128) unsigned char smem[];
+    const TileGeom g = tile_geom(prm.K, prm.C, prm.pitch, TW);
+    u64* full_bar = reinterpret_cast<u64*>(smem);              // [kStages]
+    u64* empty_bar = full_bar + kStages;                       // [kStages]
+    unsigned char* stage_base = smem + kBarBytes;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tw = warp % TW, ts = warp / TW;
-    constexpr int kThreads = TW * TS * 32;
-
     const long long p_base = prm.p_begin / kBlk * kBlk;
-    const long long P0 = p_base + (long long)blockIdx.x * (TW * kWarpTile);     // first output of the CTA
-    const long long n_lo = P0 - (long long)kBlk * g.D;                          // first input of the tile
-    const long long q0 = n_lo / kBlk;                                           // exact: n_lo % 32 == 0 (may be < 0)
-    const int spc = prm.C / kBlk;                                               // subchunks per chunk
+    const int spc = prm.C / kBlk;                              // subchunks per chunk
     const long long n_chunks = prm.n_in / prm.C;
-    // chunks touched by the tile's inputs, clamped to the signal
-    long long c_first = n_lo < 0 ? 0 : n_lo / prm.C;
-    long long c_last = (P0 + (long long)TW * kWarpTile - 1) / prm.C;
-    if (c_last > n_chunks - 1) c_last = n_chunks - 1;
-    if (c_first > c_last) c_first = c_last;
-    const int n_rows = (int)(c_last - c_first + 1);
+    const int ipu = MIX ? prm.n_src : 1;                       // pipeline items per unit of work
+    const long long n_units = MIX ? prm.tiles : prm.tiles * prm.n_src;
+    const long long my_units = blockIdx.x < n_units ? (n_units - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long n_items = my_units * ipu;
 
-    const int blk = tw * 32 + lane;                 // output block of this lane inside the CTA tile
-    // tap blocks of this warp: d in [d_first, d_last)
-    const int d_per = (g.D + 1 + TS - 1) / TS;
-    const int d_first = ts * d_per;
-    const int d_last = min(g.D + 1, d_first + d_per);
-    const bool warp_live = P0 + (long long)tw * kWarpTile < prm.p_end;
-
-    const int s_first = prm.mix ? 0 : blockIdx.y;
-    const int s_last = prm.mix ? prm.n_src : blockIdx.y + 1;
-
-    if (prm.mix) {
-        for (int i = tid; i < 2 * TW * 32 * kStagePitch; i += kThreads) stage[i] = 0.f;
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, TW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    __syncthreads();
 
-    for (int s = s_first; s < s_last; ++s) {
-        // ---- stage the input tile (zero outside [0, n_valid)) ---------------------------------
-        const float* x = prm.x + (long long)s * prm.x_stride;
-        for (int c = tid; c < g.x_rows * 8; c += kThreads) {
-            const int row = c >> 3, ch = c & 7;
-            const long long n = n_lo + (long long)row * kBlk + ch * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (n >= 0 && n + 3 < prm.n_valid) {
-                v = *reinterpret_cast<const float4*>(x + n);
-            } else if (n + 3 >= 0 && n < prm.n_valid) {
-                if (n >= 0 && n < prm.n_valid) v.x = x[n];
-                if (n + 1 >= 0 && n + 1 < prm.n_valid) v.y = x[n + 1];
-                if (n + 2 >= 0 && n + 2 < prm.n_valid) v.z = x[n + 2];
-                if (n + 3 >= 0 && n + 3 < prm.n_valid) v.w = x[n + 3];
-            }
-            xs[row * 8 + (ch ^ (row & 7))] = v;
-        }
-        // ---- stage the filter rows: {H_i, H_{i+1} - H_i} for both ears, zero padded --------------
-        const float* f = prm.filt + (long long)s * prm.filt_src_stride;
-        for (int e = tid; e < n_rows * g.row_len; e += kThreads) {
-            const int ri = e / g.row_len, idx = e - ri * g.row_len;
-            const int k = idx - kBlk;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (k >= 0 && k < prm.K) {
-                const float* h0 = f + (c_first + ri) * 2 * prm.filt_stride;
-                const float* h1 = h0 + 2 * prm.filt_stride;
-                const float l0 = h0[k], r0 = h0[prm.filt_stride + k];
-                v = make_float4(l0, r0, h1[k] - l0, h1[prm.filt_stride + k] - r0);
-            }
-            rows[e] = v;
-        }
-        __syncthreads();
+    // item j of this CTA -> (tile, source)
+    auto item_unit = [&](long long j, long long& tile, int& src) {
+        const long long unit = blockIdx.x + (j / ipu) * gridDim.x;
+        if (MIX) { tile = unit; src = (int)(j % ipu); }
+        else { src = (int)(unit / prm.tiles); tile = unit - (long long)src * prm.tiles; }
+    };
+    // chunk range whose filter rows item needs (clamped to the signal)
+    auto tile_chunks = [&](long long tile, long long& n_lo, long long& c_first, int& n_rows) {
+        const long long P0 = p_base + tile * (TW * kWarpTile);
+        n_lo = P0 - (long long)kBlk * g.D;
+        c_first = n_lo < 0 ? 0 : n_lo / prm.C;
+        long long c_last = (P0 + (long long)TW * kWarpTile - 1) / prm.C;
+        if (c_last > n_chunks - 1) c_last = n_chunks - 1;
+        if (c_first > c_last) c_first = c_last;
+        n_rows = (int)(c_last - c_first + 2);                   // + the boundary after the last chunk
+    };
 
-        // ---- the FIR ----------------------------------------------------------------------------
-        u64 acc[kBlk];
+    // ---- producer: warp 0 stages item j into ring slot j % kStages --------------------------------
+    auto produce = [&](long long j) {
+        const int st = (int)(j % kStages);
+        const long long use = j / kStages;
+        if (use > 0) mbar_wait(empty_bar + st, (unsigned)((use - 1) & 1));      // consumers left the slot
+        long long tile, n_lo, c_first; int src, n_rows;
+        item_unit(j, tile, src);
+        tile_chunks(tile, n_lo, c_first, n_rows);
+        float* xs = reinterpret_cast<float*>(stage_base + (size_t)st * g.stage_bytes);
+        float2* fs = reinterpret_cast<float2*>(stage_base + (size_t)st * g.stage_bytes + g.x_bytes);
+        const float* x = prm.x + (long long)src * prm.x_stride;
+        // rows that are not entirely inside [0, n_valid) are written by hand (zeros outside)
+        unsigned bytes = 0;
+        for (int row = lane; row < g.x_rows; row += 32) {
+            const long long n = n_lo + (long long)row * kBlk;
+            if (n >= 0 && n + kBlk <= prm.n_valid) {
+                bytes += kBlk * 4;
+            } else {
+                float* d = xs + row * kXPitch;
+#pragma unroll 4
+                for (int i = 0; i < kBlk; ++i) d[i] = (n + i >= 0 && n + i < prm.n_valid) ? x[n + i] : 0.f;
+            }
+        }
+        bytes = __reduce_add_sync(0xffffffffu, bytes);
+        __syncwarp();                                                          // hand-written rows ordered before the arrive
+        const unsigned f_bytes = (unsigned)n_rows * prm.pitch * 8;
+        if (lane == 0) {
+            mbar_arrive_expect_tx(full_bar + st, bytes + f_bytes);             // releases the hand-written rows too
+            bulk_g2s(fs, prm.filt + (long long)src * prm.filt_src_stride + c_first * prm.pitch, f_bytes, full_bar + st);
+        }
+        __syncwarp();
+        for (int row = lane; row < g.x_rows; row += 32) {
+            const long long n = n_lo + (long long)row * kBlk;
+            if (n >= 0 && n + kBlk <= prm.n_valid) bulk_g2s(xs + row * kXPitch, x + n, kBlk * 4, full_bar + st);
+        }
+    };
+
+    if (warp == 0 && n_items > 0) produce(0);
+
+    u64 acc[kBlk];
+    u64 mixacc[MIX ? kBlk : 1];
 #pragma unroll
-        for (int r = 0; r < kBlk; ++r) acc[r] = 0ull;
+    for (int r = 0; r < kBlk; ++r) acc[r] = 0ull;
+    if (MIX) {
+#pragma unroll
+        for (int r = 0; r < (MIX ? kBlk : 1); ++r) mixacc[r] = 0ull;
+    }
+    const int blk = warp * 32 + lane;                           // output block of this lane inside the tile
+    const bool vec_ok = (prm.p_begin & 3) == 0 && (prm.out_stride & 3) == 0 &&
+                        (reinterpret_cast<uintptr_t>(prm.out) & 15) == 0;
+
+    for (long long j = 0; j < n_items; ++j) {
+        if (warp == 0 && j + 1 < n_items) produce(j + 1);
+        const int st = (int)(j % kStages);
+        long long tile, n_lo, c_first; int src, n_rows;
+        item_unit(j, tile, src);
+        tile_chunks(tile, n_lo, c_first, n_rows);
+        const long long P0 = p_base + tile * (TW * kWarpTile);
+        const bool warp_live = P0 + (long long)warp * kWarpTile < prm.p_end;
+        const float* xs = reinterpret_cast<const float*>(stage_base + (size_t)st * g.stage_bytes);
+        const float2* fs = reinterpret_cast<const float2*>(stage_base + (size_t)st * g.stage_bytes + g.x_bytes);
+        const long long q0 = n_lo / kBlk;                       // exact (n_lo % 32 == 0), may be negative
+
+        mbar_wait(full_bar + st, (unsigned)((j / kStages) & 1));
+
         if (warp_live) {
-            for (int d = d_first; d < d_last; ++d) {
-                const int xrow = blk + g.D - d;                     // input row (subchunk) inside the tile
-                const long long q = q0 + xrow;                      // absolute subchunk
+            // per-lane filter row pointer and blend weight of input row `xrow`
+            auto lane_filter = [&](int xrow, const float2*& rowp, u64& alpha2) {
+                const long long q = q0 + xrow;
                 long long chunk = q < 0 ? 0 : q / spc;
                 const int sub = q < 0 ? 0 : (int)(q - chunk * spc);
-                if (chunk < c_first) chunk = c_first;               // only for rows whose samples are all zero
-                if (chunk > c_last) chunk = c_last;
-                const float alpha = (float)(sub * kBlk) / (float)prm.C;         // apply_hrtf.py:442
-                const ulonglong2* rowp = reinterpret_cast<const ulonglong2*>(rows) +
-                                         (size_t)(chunk - c_first) * g.row_len + kBlk + d * kBlk;
-                block_32x32(acc, rowp, pack2(alpha, alpha), xs + xrow * 8, xrow & 7);
+                long long ri = chunk - c_first;                  // rows outside the staged range belong
+                if (ri < 0) ri = 0;                              // to input rows that are all zero
+                if (ri > n_rows - 2) ri = n_rows - 2;
+                const float alpha = (float)(sub * kBlk) / (float)prm.C;          // apply_hrtf.py:442
+                rowp = fs + ri * prm.pitch;
+                alpha2 = pack2(alpha, alpha);
+            };
+            // d = 0 is the folded block: ring initialised from the d = 0 filter (r >= m), refilled from
+            // the d = D filter (r < m).  One call site keeps the unrolled body in the instruction cache.
+#pragma unroll 1
+            for (int d = 0; d < g.D; ++d) {
+                const float2 *ra, *rb; u64 aa, ab;
+                const int xrow_a = blk + g.D - d;
+                int xrow_b = xrow_a;
+                lane_filter(xrow_a, ra, aa);
+                ra += kBlk * d;
+                rb = ra; ab = aa;
+                if (d == 0) {
+                    xrow_b = blk;
+                    lane_filter(xrow_b, rb, ab);
+                    rb += kBlk * g.D;
+                }
+                block_32x32(acc, ra, aa, rb, ab, prm.pitch, xs + xrow_a * kXPitch, xs + xrow_b * kXPitch);
             }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar + st);             // this warp is done with the slot
 
-        // ---- combine tap splits, peak, mix -------------------------------------------------------
-        if (!prm.mix) __syncthreads();          // staging aliases rows/xs: everyone must be done reading
-        const float gain = prm.gains ? prm.gains[s] : 1.f;
-        float* my_l = stage + blk * kStagePitch;
-        float* my_r = stage + (TW * 32 + blk) * kStagePitch;
-        if (TS == 1 && !prm.mix) {
+        // ---- peak, gain, mix, store ----------------------------------------------------------------
+        const long long pb = P0 + (long long)blk * kBlk;        // first output of this lane
+        const float gain = prm.gains ? prm.gains[src] : 1.f;
+        if (prm.peaks) {
             float pk = 0.f;
-            const long long pb = P0 + (long long)blk * kBlk;
 #pragma unroll
             for (int r = 0; r < kBlk; ++r) {
                 float l, rr; unpack2(acc[r], l, rr);
-                const bool in = pb + r >= prm.p_begin && pb + r < prm.p_end;
-                if (in) pk = fmaxf(pk, fmaxf(fabsf(l), fabsf(rr)));
-                my_l[r] = gain * l; my_r[r] = gain * rr;
+                if (pb + r >= prm.p_begin && pb + r < prm.p_end) pk = fmaxf(pk, fmaxf(fabsf(l), fabsf(rr)));
             }
-            if (prm.peaks) { pk = warp_max(pk); if (lane == 0 && pk > 0.f) atomic_max_nonneg(prm.peaks + s, pk); }
-        } else {
-            // per-source tile in registers -> the tap splits take turns adding into a scratch copy
-            // (fixed order: deterministic), the last one takes the peak and folds into the mix.
-            // Scratch = lane-private slots, so only block-level ordering between turns is needed.
-            float* scr_l = my_l; float* scr_r = my_r;
-            if (prm.mix) {   // scratch for the per-source sum lives in the (now idle) input tile area
-                float* scr = reinterpret_cast<float*>(rows);
-                __syncthreads();
-                scr_l = scr + blk * kStagePitch; scr_r = scr + (TW * 32 + blk) * kStagePitch;
-            }
-            for (int turn = 0; turn < TS; ++turn) {
-                if (ts == turn) {
-                    float pk = 0.f;
-                    const long long pb = P0 + (long long)blk * kBlk;
+            pk = warp_max(pk);
+            if (lane == 0 && pk > 0.f) atomic_max_nonneg(prm.peaks + src, pk);
+        }
+        bool store = true;
+        if (MIX) {
+            const u64 g2 = pack2(gain, gain);
 #pragma unroll
-                    for (int r = 0; r < kBlk; ++r) {
-                        float l, rr; unpack2(acc[r], l, rr);
-                        if (turn > 0) { l += scr_l[r]; rr += scr_r[r]; }
-                        if (turn == TS - 1) {
-                            const bool in = pb + r >= prm.p_begin && pb + r < prm.p_end;
-                            if (in) pk = fmaxf(pk, fmaxf(fabsf(l), fabsf(rr)));
-                            if (prm.mix) { my_l[r] = fmaf(gain, l, my_l[r]); my_r[r] = fmaf(gain, rr, my_r[r]); }
-                            else { my_l[r] = gain * l; my_r[r] = gain * rr; }
-                        } else { scr_l[r] = l; scr_r[r] = rr; }
+            for (int r = 0; r < kBlk; ++r) { mixacc[r & (MIX ? 31 : 0)] = fma2(g2, acc[r], mixacc[r & (MIX ? 31 : 0)]); acc[r] = 0ull; }
+            store = (j % ipu) == ipu - 1;
+        }
+        if (store) {
+            float* o = prm.out + (MIX ? 0 : (long long)src * 2 * prm.out_stride);
+            const long long off = pb - prm.p_begin;
+            if (vec_ok && pb >= prm.p_begin && pb + kBlk <= prm.p_end) {
+#pragma unroll
+                for (int r4 = 0; r4 < kBlk; r4 += 4) {
+                    float l[4], rr[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        unpack2(MIX ? mixacc[(r4 + i) & (MIX ? 31 : 0)] : acc[r4 + i], l[i], rr[i]);
+                        if (!MIX) { l[i] *= gain; rr[i] *= gain; }
                     }
-                    if (turn == TS - 1 && prm.peaks) {
-                        pk = warp_max(pk);
-                        if (lane == 0 && pk > 0.f) atomic_max_nonneg(prm.peaks + s, pk);
-                    }
+                    *reinterpret_cast<float4*>(o + off + r4) = make_float4(l[0], l[1], l[2], l[3]);
+                    *reinterpret_cast<float4*>(o + prm.out_stride + off + r4) = make_float4(rr[0], rr[1], rr[2], rr[3]);
                 }
-                if (turn + 1 < TS) __syncthreads();
+            } else {
+#pragma unroll
+                for (int r = 0; r < kBlk; ++r) {
+                    float l, rr; unpack2(MIX ? mixacc[r & (MIX ? 31 : 0)] : acc[r], l, rr);
+                    if (!MIX) { l *= gain; rr *= gain; }
+                    if (pb + r >= prm.p_begin && pb + r < prm.p_end) { o[off + r] = l; o[prm.out_stride + off + r] = rr; }
+                }
             }
-        }
-        __syncthreads();
-
-        // ---- store (one source per CTA) ------------------------------------------------------------
-        if (!prm.mix) {
-            float* o = prm.out + (long long)s * 2 * prm.out_stride;
-            for (int i = tid; i < 2 * TW * kWarpTile; i += kThreads) {
-                const int e = i / (TW * kWarpTile), idx = i - e * (TW * kWarpTile);
-                const long long p = P0 + idx;
-                if (p >= prm.p_begin && p < prm.p_end)
-                    o[e * prm.out_stride + (p - prm.p_begin)] = stage[(e * TW * 32 + (idx >> 5)) * kStagePitch + (idx & 31)];
+#pragma unroll
+            for (int r = 0; r < kBlk; ++r) acc[r] = 0ull;
+            if (MIX) {
+#pragma unroll
+                for (int r = 0; r < (MIX ? kBlk : 1); ++r) mixacc[r] = 0ull;
             }
-        }
-    }
-    if (prm.mix) {
-        for (int i = tid; i < 2 * TW * kWarpTile; i += kThreads) {
-            const int e = i / (TW * kWarpTile), idx = i - e * (TW * kWarpTile);
-            const long long p = P0 + idx;
-            if (p >= prm.p_begin && p < prm.p_end)
-                prm.out[e * prm.out_stride + (p - prm.p_begin)] = stage[(e * TW * 32 + (idx >> 5)) * kStagePitch + (idx & 31)];
         }
     }
 }
 
-template <int TW, int TS>
-int launch_tiled(const RenderParams& prm, cudaStream_t st) {
-    const TileGeom g = tile_geom(prm.K, prm.C, TW);
-    const size_t smem = tile_smem_bytes(g, TW, prm.mix != 0);
+template <int TW, bool MIX>
+int launch_tiled(RenderParams prm, cudaStream_t st) {
+    const TileGeom g = tile_geom(prm.K, prm.C, prm.pitch, TW);
+    const size_t smem = kBarBytes + (size_t)kStages * g.stage_bytes;
     if (smem > 227 * 1024) return BAS_E_UNSUPPORTED;
-    auto kern = bas_render_tiled_kernel<TW, TS>;
+    auto kern = bas_render_tiled_kernel<TW, MIX>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { bas_set_error("bas_render: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     const long long p_base = prm.p_begin / kBlk * kBlk;
-    const long long tiles = bas_ceil_div(prm.p_end - p_base, (long long)TW * kWarpTile);
-    if (tiles > 0x7fffffffLL || prm.n_src > 65535) return BAS_E_UNSUPPORTED;
-    dim3 grid((unsigned)tiles, prm.mix ? 1u : (unsigned)prm.n_src);
-    kern<<<grid, TW * TS * 32, smem, st>>>(prm);
+    prm.tiles = bas_ceil_div(prm.p_end - p_base, (long long)TW * kWarpTile);
+    const long long units = prm.mix ? prm.tiles : prm.tiles * prm.n_src;
+    // persistent grid: as many CTAs as the device keeps resident
+    static thread_local int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    }
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TW * 32, smem);
+    if (e != cudaSuccess || per_sm < 1) { bas_set_error("bas_render: tile shape does not fit an SM"); cudaGetLastError(); return BAS_E_UNSUPPORTED; }
+    long long grid = (long long)sm_count * per_sm;
+    if (grid > units) grid = units;
+    kern<<<(unsigned)grid, TW * 32, smem, st>>>(prm);
     e = cudaGetLastError();
     if (e != cudaSuccess) { bas_set_error("bas_render: tiled launch failed: %s", cudaGetErrorString(e)); return (int)e; }
     return 0;
@@ -393,16 +482,16 @@ bas_normalise_kernel(float* __restrict__ v, long long n, const float* __restrict
 
 }  // namespace
 
-// variant encoding beyond the public three: BAS_RENDER_TILED | (TW << 8) | (TS << 16) picks a tile shape
-// (used by the tuning sweep in bench.py; unknown shapes return BAS_E_UNSUPPORTED).
+// variant encoding beyond the public three: BAS_RENDER_TILED | (TW << 8) picks the warps per CTA
+// (tuning sweeps; unknown shapes return BAS_E_UNSUPPORTED).
 extern "C" int bas_render(const float* x_dev, long long x_stride, long long n_valid, int n_src, long long n_in,
-                          int C, int S, int K, const float* filt_dev, long long filt_stride, const float* gains_dev,
+                          int C, int S, int K, const float* filt_dev, const float* gains_dev,
                           long long p_begin, long long p_count, float* out_dev, long long out_stride, int mix,
                           float* peaks_dev, int variant, void* stream) {
     BAS_CHECK_ARG(x_dev && filt_dev && out_dev, "null pointer");
     BAS_CHECK_ARG(n_src >= 1, "n_src");
     BAS_CHECK_ARG(C >= 1 && S >= 1 && C % S == 0, "subchunksize must divide chunksize");     // apply_hrtf.py:401-402
-    BAS_CHECK_ARG(K >= 1 && filt_stride >= K, "need 1 <= K <= filt_stride");
+    BAS_CHECK_ARG(K >= 1 && K < (1 << 20), "K");
     BAS_CHECK_ARG(n_in >= C && n_in % C == 0, "n_in must be a positive multiple of C");      // apply_hrtf.py:405
     BAS_CHECK_ARG(n_valid >= 0 && n_valid <= n_in && (n_src == 1 || x_stride >= n_valid), "n_valid / x_stride");
     BAS_CHECK_ARG(p_begin >= 0 && p_count >= 0 && p_begin + p_count <= n_in + K - 1, "output range");
@@ -411,32 +500,34 @@ extern "C" int bas_render(const float* x_dev, long long x_stride, long long n_va
     cudaStream_t st = (cudaStream_t)stream;
     RenderParams prm;
     prm.x = x_dev; prm.x_stride = x_stride; prm.n_valid = n_valid; prm.n_src = n_src; prm.n_in = n_in;
-    prm.C = C; prm.S = S; prm.K = K; prm.filt = filt_dev; prm.filt_stride = filt_stride;
-    prm.filt_src_stride = (n_in / C + 1) * 2 * filt_stride;
+    prm.C = C; prm.S = S; prm.K = K; prm.filt = reinterpret_cast<const float2*>(filt_dev);
+    prm.pitch = bas_filter_row_pitch(K);
+    prm.filt_src_stride = (n_in / C + 1) * (long long)prm.pitch;
     prm.gains = gains_dev; prm.p_begin = p_begin; prm.p_end = p_begin + p_count;
-    prm.out = out_dev; prm.out_stride = out_stride; prm.mix = mix ? 1 : 0; prm.peaks = peaks_dev;
+    prm.out = out_dev; prm.out_stride = out_stride; prm.mix = mix ? 1 : 0; prm.peaks = peaks_dev; prm.tiles = 0;
 
     const int base = variant & 0xff;
     BAS_CHECK_ARG(base == BAS_RENDER_AUTO || base == BAS_RENDER_GENERIC || base == BAS_RENDER_TILED, "variant");
-    const bool tiled_ok = S == kBlk && C % kBlk == 0 && K <= 1024 &&
-                          (reinterpret_cast<uintptr_t>(x_dev) & 15) == 0 && (n_src == 1 || x_stride % 4 == 0);
+    const bool tiled_ok = S == kBlk && C % kBlk == 0 && (reinterpret_cast<uintptr_t>(x_dev) & 15) == 0 &&
+                          (reinterpret_cast<uintptr_t>(filt_dev) & 15) == 0 && (n_src == 1 || x_stride % 4 == 0);
     if (base == BAS_RENDER_TILED && !tiled_ok) {
-        bas_set_error("bas_render: tiled kernel needs S == 32, 32 | C, K <= 1024, 16-byte aligned signals");
+        bas_set_error("bas_render: tiled kernel needs S == 32, 32 | C, 16-byte aligned signals and filter rows");
         return BAS_E_UNSUPPORTED;
     }
     if (base != BAS_RENDER_GENERIC && tiled_ok) {
-        int tw = (variant >> 8) & 0xff, tsp = (variant >> 16) & 0xff;
-        if (tw == 0 && tsp == 0) {
-            // default shapes: many small CTAs when one source must fill the GPU, larger tiles for a mix
-            if (prm.mix) { tw = 2; tsp = 3; } else { tw = 1; tsp = 3; }
-        }
+        const int tw_req = (variant >> 8) & 0xff;
         int rc = BAS_E_UNSUPPORTED;
-#define BAS_TILE_CASE(TW_, TS_) if (tw == TW_ && tsp == TS_) rc = launch_tiled<TW_, TS_>(prm, st)
-        BAS_TILE_CASE(1, 1); BAS_TILE_CASE(1, 3); BAS_TILE_CASE(2, 1); BAS_TILE_CASE(2, 3); BAS_TILE_CASE(4, 1);
-        BAS_TILE_CASE(1, 2); BAS_TILE_CASE(2, 2); BAS_TILE_CASE(4, 2); BAS_TILE_CASE(1, 4);
-#undef BAS_TILE_CASE
+        // default: 4 warps per CTA, falling back to smaller tiles when shared memory runs out
+        const int order[3] = {tw_req ? tw_req : 4, tw_req ? 0 : 2, tw_req ? 0 : 1};
+        for (int i = 0; i < 3 && rc == BAS_E_UNSUPPORTED; ++i) {
+            const int tw = order[i];
+            if (tw == 8) rc = prm.mix ? launch_tiled<8, true>(prm, st) : launch_tiled<8, false>(prm, st);
+            else if (tw == 4) rc = prm.mix ? launch_tiled<4, true>(prm, st) : launch_tiled<4, false>(prm, st);
+            else if (tw == 2) rc = prm.mix ? launch_tiled<2, true>(prm, st) : launch_tiled<2, false>(prm, st);
+            else if (tw == 1) rc = prm.mix ? launch_tiled<1, true>(prm, st) : launch_tiled<1, false>(prm, st);
+        }
         if (rc != BAS_E_UNSUPPORTED || base == BAS_RENDER_TILED) {
-            if (rc == BAS_E_UNSUPPORTED) bas_set_error("bas_render: tile shape %dx%d unavailable for K=%d C=%d", tw, tsp, K, C);
+            if (rc == BAS_E_UNSUPPORTED) bas_set_error("bas_render: no tile shape fits K=%d C=%d (requested TW=%d)", K, C, tw_req);
             return rc;
         }
     }

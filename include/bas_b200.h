@@ -102,18 +102,26 @@ int bas_plan_ring_host(const double* diffs_left, const double* diffs_right, int 
 /* ---- IR synthesis: the array part of interpolate_2d (apply_hrtf.py:219-281) and of
  *      delay_compensated_interpolation_with_delaydiff (apply_hrtf.py:86-102) ------------------
  * bank_pp_dev: 2 x 187 x U x K floats (left ear block, then right), polyphase.
- * decimate=1: out[point][ear][m], m < K, row stride out_stride >= K floats (tail zero-filled);
- * decimate=0: out[point][ear][n], n < K*U (return_upsampled=True). */
+ * mode BAS_IR_UPSAMPLED: out[point][ear][n], n < K*U  (return_upsampled=True), row stride out_stride;
+ * mode BAS_IR_PLANAR:    out[point][ear][m], m < K, row stride out_stride >= K floats (tail zeroed);
+ * mode BAS_IR_ROWS:      out[point][m][ear], m < bas_filter_row_pitch(K) (taps >= K zeroed): the
+ *                        filter-row layout bas_render consumes; out_stride is ignored. */
+#define BAS_IR_UPSAMPLED 0
+#define BAS_IR_PLANAR 1
+#define BAS_IR_ROWS 2
 int bas_ir_synth(const float* bank_pp_dev, int U, int K, const bas_term* terms_dev, long long n_points,
-                 int decimate, float* out_dev, long long out_stride, void* stream);
+                 int mode, float* out_dev, long long out_stride, void* stream);
+
+/* Taps per filter row in the BAS_IR_ROWS layout: K rounded up to a multiple of 32, plus 2 (the
+ * row pitch in bytes, 8 * pitch, is a multiple of 16 but not of 128). */
+int bas_filter_row_pitch(int K);
 
 /* ---- renderer: the chunk/subchunk loops of make_signal_move_2d, apply_hrtf.py:431-453 --------
  * Output-stationary form of the overlap-add:
  *     out_e[p] = sum_k x[p-k] * h_{q(p-k),e}[k],   h_q = (1-alpha_q) H_i + alpha_q H_{i+1}
  * x_dev:     n_src signals, x_stride floats apart; samples >= n_valid are treated as zero (the
  *            zero padding to n_in of apply_hrtf.py:405-406 is implicit).
- * filt_dev:  n_src x (n_in/C + 1) x 2 x filt_stride boundary filters from bas_ir_synth
- *            (filt_stride >= K; the tiled kernel needs filt_stride % 4 == 0).
+ * filt_dev:  n_src x (n_in/C + 1) filter rows in the BAS_IR_ROWS layout (16-byte aligned).
  * gains_dev: n_src floats multiplying each source before mixing, or NULL for 1.
  * Output samples p_begin <= p < p_begin + p_count (0 <= p, p_begin + p_count <= n_in + K - 1):
  * out_dev:   mix=0: n_src x 2 x out_stride (planar L then R), out[s][e][p - p_begin];
@@ -121,12 +129,12 @@ int bas_ir_synth(const float* bank_pp_dev, int U, int K, const bas_term* terms_d
  * peaks_dev: n_src floats, max |out| of each source over the rendered range BEFORE gain and mixing
  *            (for apply_hrtf.py:462), or NULL.  Must be zeroed by the caller (atomic max).
  * variant:   BAS_RENDER_AUTO / _GENERIC (any C, S, K) / _TILED (needs S == 32, C % 32 == 0,
- *            K <= 1024; BAS_E_UNSUPPORTED otherwise). */
+ *            16-byte aligned signals; BAS_E_UNSUPPORTED otherwise). */
 #define BAS_RENDER_AUTO 0
 #define BAS_RENDER_GENERIC 1
 #define BAS_RENDER_TILED 2
 int bas_render(const float* x_dev, long long x_stride, long long n_valid, int n_src, long long n_in,
-               int C, int S, int K, const float* filt_dev, long long filt_stride, const float* gains_dev,
+               int C, int S, int K, const float* filt_dev, const float* gains_dev,
                long long p_begin, long long p_count, float* out_dev, long long out_stride, int mix,
                float* peaks_dev, int variant, void* stream);
 

@@ -1,0 +1,237 @@
+"""Parity of the CUDA path (through the Python call surface -> C ABI -> sm_100a kernels) against the
+oracle and the committed reference vectors.  Tolerances are BASELINE.json's: integer indices
+bit-exact; fp32 output within relative L2 error 1e-5 and max-abs error 1e-5 of peak."""
+import numpy as np
+import pytest
+
+from .conftest import as_kind, golden_trajectory, rel_l2, max_abs_over_peak, KIND_PY, KIND_F64, KIND_F32
+
+pytestmark = pytest.mark.gpu
+
+REL_L2 = 1e-5
+MAX_ABS = 1e-5
+
+
+def close(got, want):
+    assert got.shape == want.shape, (got.shape, want.shape)
+    assert rel_l2(got, want) <= REL_L2, rel_l2(got, want)
+    assert max_abs_over_peak(got, want) <= MAX_ABS, max_abs_over_peak(got, want)
+
+
+def test_extension_loaded_and_device_present(bas):
+    import torch
+    assert torch.cuda.is_available()
+    assert bas._cabi.lib.bas_device_count() >= 1
+    assert torch.cuda.get_device_capability(0)[0] == 10
+
+
+def test_interpolate_2d_vs_golden(bas, golden, golden_bank):
+    for (elev, azim, kind), want in zip(golden['dir_cases'], golden['dir_irs']):
+        got = bas.interpolate_2d(golden_bank, elev, as_kind(azim, kind))
+        assert got.dtype == np.float64
+        close(got, want)
+
+
+def test_interpolate_2d_batch_device_plan_bit_exact(bas, golden, golden_bank):
+    """The fp64 device plan kernel gives the same integers as the reference (and as its host twin)."""
+    cases = golden['dir_cases']
+    kinds = cases[:, 2].astype(np.uint8)
+    filt, trace = bas.interpolate_2d_batch(golden_bank, cases[:, 0], cases[:, 1], kinds, return_trace=True)
+    _, host_trace = bas.plan_points_host(golden_bank, cases[:, 0], cases[:, 1], kinds)
+    for name in ('rows', 'lo', 'hi', 'err'):
+        assert np.array_equal(trace[name], host_trace[name]), name
+    for name in ('alpha_top', 'alpha_bot', 'a'):
+        assert np.array_equal(trace[name], host_trace[name]), name
+    for i, delays in enumerate(golden['dir_delays']):
+        for ear in range(2):
+            order = [0 + ear, 2 + ear, 4 + ear, 6 + ear, 8 + ear, 10 + ear]
+            assert list(trace['lo'][i, ear]) == [int(np.floor(delays[j])) for j in order]
+            assert list(trace['hi'][i, ear]) == [int(np.ceil(delays[j])) for j in order]
+    close(filt.cpu().numpy().astype(np.float64), golden['dir_irs'])
+
+
+def test_interpolate_2d_random_vs_oracle(bas, oracle, synth_bank):
+    rng = np.random.default_rng(101)
+    elev = rng.uniform(-1.2, 1.9, 64)
+    azim = rng.uniform(-10, 20, 64)
+    filt = bas.interpolate_2d_batch(synth_bank, elev, azim, KIND_F64).cpu().numpy()
+    for i in range(64):
+        close(filt[i].astype(np.float64), oracle.interpolate_2d(synth_bank, elev[i], np.float64(azim[i])))
+
+
+def test_interpolate_2d_known_answers(bas, synth_bank):
+    """alpha = 0 on a grid ring returns the decimated bank row."""
+    u = synth_bank.upsampling
+    got = bas.interpolate_2d(synth_bank, 0.0, 0.0)          # row 72 exactly
+    want = np.vstack([synth_bank.irs_left[72, ::u], synth_bank.irs_right[72, ::u]])
+    close(got, want)
+    got = bas.interpolate_2d(synth_bank, np.pi / 2, 1.234)  # the pole: row 186 whatever the azimuth
+    want = np.vstack([synth_bank.irs_left[186, ::u], synth_bank.irs_right[186, ::u]])
+    close(got, want)
+
+
+def test_interpolate_2d_errors(bas, golden_bank):
+    with pytest.raises(AssertionError):
+        bas.interpolate_2d(golden_bank, float('nan'), 1.0)       # apply_hrtf.py:266
+    with pytest.raises(AssertionError):
+        bas.interpolate_2d(golden_bank, 0.2, float('nan'))       # sphere.py:87
+    with pytest.raises(AssertionError):
+        bas.interpolate_2d_batch(golden_bank, [0.1, 0.2], [1.0, float('nan')])
+
+
+def test_ring_interpolation_vs_golden(bas, golden, golden_bank):
+    for (b, a, alpha), dec, up, (dl, dr) in zip(golden['ringinterp_in'], golden['ringinterp_dec'],
+                                                golden['ringinterp_up'], golden['ringinterp_delays']):
+        got = bas.delay_compensated_interpolation_with_delaydiff(golden_bank, int(b), int(a), float(alpha))
+        assert got[0] == dl and got[1] == dr            # float64 scalars: exact
+        close(got[2], dec)
+        got_up = bas.delay_compensated_interpolation_with_delaydiff(golden_bank, int(b), int(a), float(alpha), True)
+        close(got_up[2], up)
+    with pytest.raises(IndexError):
+        bas.delay_compensated_interpolation_with_delaydiff(golden_bank, 187, 0, 0.5)
+
+
+@pytest.mark.parametrize('variant', ['auto', 'generic'])
+def test_make_signal_move_2d_vs_golden(bas, golden, golden_bank, variant):
+    k = float(golden['render_k'])
+    bas.apply_hrtf.PROGRESS = False
+    for i in range(int(golden['n_renders'])):
+        n, c, s = (int(v) for v in golden['render%d_meta' % i])
+        traj = golden_trajectory(golden['render%d_traj' % i], k)
+        x = golden['render%d_x' % i]
+        if variant == 'auto':
+            got = bas.make_signal_move_2d(x, c, s, traj, golden_bank)
+            assert got.shape[1] == 2 and got.dtype == np.float32 and got.flags.f_contiguous
+        else:
+            got = bas.render_sources(x[None], c, s, [traj], golden_bank, variant=bas._cabi.RENDER_GENERIC)[0].T
+        close(got, golden['render%d_y' % i])
+
+
+def _traj(seed, fs=44100.0):
+    rng = np.random.default_rng(seed)
+    f1, f2, p1, p2 = rng.uniform(0.5, 3.0), rng.uniform(0.5, 3.0), rng.uniform(0, 6), rng.uniform(0, 6)
+    k = 2 * np.pi / fs
+
+    def fn(t):
+        return (np.deg2rad(22.5 + 67.5 * np.sin(f1 * 40 * k * t + p1)), (f2 * 60 * k * t + p2) % (2 * np.pi))
+    return fn
+
+
+@pytest.mark.parametrize('tw', [1, 2, 4, 8])
+def test_tiled_shapes_vs_oracle(bas, oracle, synth_bank, tw):
+    """Every compiled tile shape (warps per CTA) of the register-tiled kernel, K = 256."""
+    rng = np.random.default_rng(5)
+    n = 9000
+    x = (0.05 * rng.standard_normal(n)).astype(np.float32)
+    traj = _traj(3)
+    want = oracle.make_signal_move_2d(x, 512, 32, traj, synth_bank)
+    variant = bas._cabi.RENDER_TILED | (tw << 8)
+    got = bas.render_sources(x[None], 512, 32, [traj], synth_bank, variant=variant)[0].T
+    close(got, want)
+
+
+@pytest.mark.parametrize('k_taps,c,n', [(100, 512, 5000), (256, 128, 4000), (33, 64, 1500), (512, 512, 6000), (1, 32, 200)])
+def test_tiled_odd_geometries_vs_oracle(bas, oracle, k_taps, c, n):
+    """samples_to_keep that is not a multiple of 32 (the reference's default is 100), small chunks,
+    a one-tap filter."""
+    f = bas.bank_synth.build_bank(8, seed=0)
+    from .conftest import GoldenBank
+    bank = GoldenBank(8, f['diffs_left'], f['diffs_right'], f['irs_left'][:, :k_taps * 8], f['irs_right'][:, :k_taps * 8])
+    rng = np.random.default_rng(k_taps)
+    x = (0.05 * rng.standard_normal(n)).astype(np.float32)
+    traj = _traj(k_taps)
+    want = oracle.make_signal_move_2d(x, c, 32, traj, bank)
+    got = bas.render_sources(x[None], c, 32, [traj], bank, variant=bas._cabi.RENDER_TILED)[0].T
+    close(got, want)
+    got = bas.render_sources(x[None], c, 32, [traj], bank, variant=bas._cabi.RENDER_GENERIC)[0].T
+    close(got, want)
+
+
+def test_upsampling_16_bank(bas, oracle):
+    """BASELINE.json config 5 shape: N=16 bank, full-length IRs (K = 512)."""
+    from .conftest import GoldenBank
+    f = bas.bank_synth.build_bank(16, seed=0)
+    bank = GoldenBank(16, f['diffs_left'], f['diffs_right'], f['irs_left'], f['irs_right'])
+    rng = np.random.default_rng(55)
+    x = (0.05 * rng.standard_normal(4000)).astype(np.float32)
+    traj = _traj(9)
+    close(bas.make_signal_move_2d(x, 512, 32, traj, bank), oracle.make_signal_move_2d(x, 512, 32, traj, bank))
+
+
+def test_batch_and_mix_vs_oracle(bas, oracle, synth_bank):
+    rng = np.random.default_rng(21)
+    n_src, n = 5, 6000
+    x = (0.02 * rng.standard_normal((n_src, n))).astype(np.float32)
+    x[3] *= 400.0                                            # this source peaks above 1 -> normalised on its own
+    trajs = [_traj(100 + s) for s in range(n_src)]
+    want = [oracle.make_signal_move_2d(x[s], 512, 32, trajs[s], synth_bank).T for s in range(n_src)]
+    got = bas.render_sources(x, 512, 32, trajs, synth_bank)
+    for s in range(n_src):
+        close(got[s], want[s])
+    assert abs(np.abs(got[3]).max() - 1.0) < 1e-6
+    mix, peaks = bas.render_sources(x, 512, 32, trajs, synth_bank, mix=True, return_peaks=True)
+    close(mix, np.sum(np.stack(want).astype(np.float64), axis=0))
+    assert peaks[3] > 1 and (np.delete(peaks, 3) < 1).all()
+    mix_generic = bas.render_sources(x, 512, 32, trajs, synth_bank, mix=True, variant=bas._cabi.RENDER_GENERIC)
+    close(mix_generic, np.sum(np.stack(want).astype(np.float64), axis=0))
+
+
+def test_time_range_windows(bas, synth_bank):
+    rng = np.random.default_rng(31)
+    x = (0.05 * rng.standard_normal((1, 7000))).astype(np.float32)
+    traj = [_traj(4)]
+    full = bas.render_sources(x, 512, 32, traj, synth_bank, normalise=False)
+    for p0, p1 in [(0, 1), (1, 1000), (777, 4099), (4096, 7423), (7000, 7423)]:
+        part = bas.render_sources(x, 512, 32, traj, synth_bank, normalise=False, time_range=(p0, p1))
+        assert np.array_equal(part, full[:, :, p0:p1])      # same kernel, same order of operations
+
+
+def test_edge_cases(bas, oracle, golden_bank):
+    bas.apply_hrtf.PROGRESS = False
+    traj = lambda t: (0, (0.01 * t) % (2 * np.pi))
+    # shorter than one chunk, exactly one chunk, impulse (output = first boundary filter)
+    for n in (1, 31, 512, 513):
+        x = np.zeros(n, dtype=np.float32); x[0] = 1.0
+        got = bas.make_signal_move_2d(x, 512, 32, traj, golden_bank)
+        want = oracle.make_signal_move_2d(x, 512, 32, traj, golden_bank)
+        close(got, want)
+        assert got.shape == (int(np.ceil(n / 512)) * 512 + 31, 2)            # apply_hrtf.py:410
+    h0 = oracle.interpolate_2d(golden_bank, 0, 0.0)
+    x = np.zeros(40, dtype=np.float32); x[0] = 0.5           # peak stays below 1: no normalisation
+    got = bas.make_signal_move_2d(x, 512, 32, traj, golden_bank)
+    close(got[:32].T.astype(np.float64), 0.5 * h0)
+    with pytest.raises(AssertionError):
+        bas.make_signal_move_2d(np.zeros((4, 2), dtype=np.float32), 512, 32, traj, golden_bank)   # mono only (:398)
+    with pytest.raises(AssertionError):
+        bas.make_signal_move_2d(np.zeros(100, dtype=np.float32), 512, 100, traj, golden_bank)    # S | C (:401-402)
+    with pytest.raises(AssertionError):
+        bas.make_signal_move_2d(np.zeros(1000, dtype=np.float32), 512, 32, lambda t: (0, float('nan')), golden_bank)
+
+
+def test_vectorised_trajectory_equals_scalar(bas, synth_bank):
+    rng = np.random.default_rng(41)
+    x = (0.05 * rng.standard_normal(5000)).astype(np.float32)
+    k = 2 * np.pi / 2000
+
+    def scalar(t):
+        return (np.float64(0.4 * np.sin(k * t)), np.float64((3 * k * t) % (2 * np.pi)))
+
+    def vec(t):
+        return (0.4 * np.sin(k * t), (3 * k * t) % (2 * np.pi))
+    vec.vectorized = True
+    a = bas.render_sources(x[None], 512, 32, [scalar], synth_bank)
+    b = bas.render_sources(x[None], 512, 32, [vec], synth_bank)
+    assert np.array_equal(a, b)
+
+
+def test_load_irs_and_delaydiffs_roundtrip(bas, tmp_path, golden_bank):
+    """The loader reads the .mat layout upsample_irs.m writes (struct irs_and_delaydiffs, v5)."""
+    path = str(tmp_path / 'bank.mat')
+    bas.bank_synth.write_mat(path, dict(upsampling=8.0, diffs_left=golden_bank.diffs_left, diffs_right=golden_bank.diffs_right,
+                                        irs_left=golden_bank.irs_left, irs_right=golden_bank.irs_right))
+    bank = bas.load_irs_and_delaydiffs(path, samples_to_keep=16)
+    assert bank.upsampling == 8 and isinstance(bank.upsampling, int)
+    assert bank.irs_left.shape == (187, 128) and bank.diffs_right.shape == (187, 187)
+    assert np.array_equal(bank.irs_left, golden_bank.irs_left[:, :128])
+    got = bas.interpolate_2d(bank, 0.3, 2.0)
+    assert got.shape == (2, 16)
