@@ -42,21 +42,41 @@ extern "C" int bas_device_count(void) {
 }
 
 // ---- device kernel ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+// One thread per (trajectory point, ear): the ear-independent ring lookups are recomputed by both
+// threads of a point (cheap) so that all 2*n_points threads run independently; 64-thread CTAs spread
+// a 5169-point trajectory over every SM.
+__global__ void __launch_bounds__(64)
 bas_plan_kernel(const double* __restrict__ diffs_l, const double* __restrict__ diffs_r, int U, long long L,
                 const double* __restrict__ elev, const double* __restrict__ azim,
                 const uint8_t* __restrict__ az_kind, int az_kind_all, long long n_points,
                 BasTerm* __restrict__ terms, BasTrace* __restrict__ trace, int* __restrict__ status) {
-    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long p = t >> 1;
+    const int ear = (int)(t & 1);
     if (p >= n_points) return;
     const int kind = az_kind ? (int)az_kind[p] : az_kind_all;
-    BasTerm local[2 * BAS_MAX_TERMS];
-    const int err = bas_plan_point(diffs_l, diffs_r, U, L, elev[p], azim[p], kind, local, trace ? trace + p : nullptr);
-    // 2 x 16 x 8 B = 256 B per point, written as 16 x 16 B
-    int4* dst = reinterpret_cast<int4*>(terms + p * 2 * BAS_MAX_TERMS);
-    const int4* src = reinterpret_cast<const int4*>(local);
+    const BasPointGeom g = bas_point_geom(elev[p], azim[p], kind);
+    BasTerm local[BAS_MAX_TERMS];
+    long long lo[6], hi[6];
+    const int err = g.err | bas_plan_point_ear(ear ? diffs_r : diffs_l, U, L, g, local, lo, hi);
+    // 16 x 8 B = 128 B per (point, ear), written as 8 x 16 B
+    int4* dst = reinterpret_cast<int4*>(terms + (p * 2 + ear) * BAS_MAX_TERMS);
 #pragma unroll
-    for (int i = 0; i < BAS_MAX_TERMS; ++i) dst[i] = src[i];
+    for (int i = 0; i < BAS_MAX_TERMS / 2; ++i)
+        dst[i] = make_int4(local[2 * i].row_shift, __float_as_int(local[2 * i].weight),
+                           local[2 * i + 1].row_shift, __float_as_int(local[2 * i + 1].weight));
+    if (trace) {
+        BasTrace* tr = trace + p;
+        if (ear == 0) {
+            tr->rows[0] = g.top.before; tr->rows[1] = g.top.after; tr->rows[2] = g.bot.before; tr->rows[3] = g.bot.after;
+            tr->alpha_top = g.top.alpha; tr->alpha_bot = g.bot.alpha; tr->a = g.a; tr->pad = 0;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { tr->lo[ear][i] = lo[i]; tr->hi[ear][i] = hi[i]; }
+        if (ear == 0) tr->err = 0;
+        __syncwarp();
+        if (err) atomicOr(&tr->err, err);
+    }
     if (err && status) {
         atomicOr(status, err);
         atomicMin(status + 1, (int)(p > INT_MAX ? INT_MAX : p));
@@ -78,8 +98,8 @@ extern "C" int bas_plan_build(const double* diffs_left_dev, const double* diffs_
         BAS_CUDA(cudaMemsetAsync(status_dev, 0, sizeof(int), st));
         BAS_CUDA(cudaMemsetAsync(status_dev + 1, 0x7f, sizeof(int), st));
     }
-    const int threads = 128;
-    const long long blocks = bas_ceil_div(n_points, threads);
+    const int threads = 64;
+    const long long blocks = bas_ceil_div(2 * n_points, threads);
     BAS_CHECK_ARG(blocks < 0x7fffffffLL, "too many points for one launch");
     bas_plan_kernel<<<(unsigned)blocks, threads, 0, st>>>(
         diffs_left_dev, diffs_right_dev, U, (long long)L, elev_dev, azim_dev, az_kind_dev, az_kind_all, n_points,

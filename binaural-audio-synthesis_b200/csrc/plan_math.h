@@ -148,67 +148,79 @@ BAS_HD BasDelay bas_split_delay(double d, int* err) {
     return s;
 }
 
-struct BasRawTerm { int row; long long shift; double w; };
+// ---- gather terms ---------------------------------------------------------------------------
+// A two-tap fractional delay by d is the polynomial P(z) = (1-f) + f z in the shift operator z,
+// anchored at shift floor(d) (apply_hrtf.py:149-165; when d is an integer f = 0 and the second tap,
+// which the reference places at ceil(d) = floor(d), carries weight zero).  Chained delays multiply
+// their polynomials and add their anchors, so each bank row contributes a short run of CONSECUTIVE
+// shifts whose weights are the coefficients of a product of 2..4 such polynomials:
+//     ring:  before row   (1-alpha)    P_restore                 2 shifts   (apply_hrtf.py:90-102)
+//            after row     alpha       P_restore P_remove        3 shifts   (apply_hrtf.py:86-102)
+//     2-D :  top rows      a           P_vrestore x ring         3 + 4      (apply_hrtf.py:268-277)
+//            bottom rows  (1-a)        P_vrestore P_vremove x ring   4 + 5  (apply_hrtf.py:254-277)
+// 16 terms per ear, in fixed slots, with no searching or merging.
+struct BasPoly2 { double c0, c1; };                          // (1-f) + f z
+BAS_HD BasPoly2 bas_poly(const BasDelay& d) { BasPoly2 p; p.c0 = 1.0 - d.frac; p.c1 = d.frac; return p; }
 
-// The six gather terms of one ring interpolation (apply_hrtf.py:82-102), and the delay it
-// reports back in base-rate samples (:106).
-BAS_HD double bas_ring_terms(const double* diffs, int upsampling, const BasRing& rg, BasRawTerm* t,
-                             long long* lo, long long* hi, int* err) {
-    const double d = (double)upsampling * diffs[rg.before * BAS_N_DIR + rg.after];   // :82-83
-    const BasDelay rem = bas_split_delay(-d, err);                                   // :86-87
-    const double d_back = rg.alpha * d;                                              // :94-95
-    const BasDelay res = bas_split_delay(d_back, err);                               // :98-102
-    lo[0] = rem.lo; hi[0] = rem.hi; lo[1] = res.lo; hi[1] = res.hi;
-    const double w2[2] = {1.0 - res.frac, res.frac};
-    const long long s2[2] = {res.lo, res.hi};
-    const double w1[2] = {1.0 - rem.frac, rem.frac};
-    const long long s1[2] = {rem.lo, rem.hi};
-    int n = 0;
-    for (int i = 0; i < 2; ++i) {
-        t[n].row = rg.before; t[n].shift = s2[i]; t[n].w = w2[i] * rg.one_minus_alpha; ++n;
-        for (int j = 0; j < 2; ++j) {
-            t[n].row = rg.after; t[n].shift = s2[i] + s1[j]; t[n].w = w2[i] * (rg.alpha * w1[j]); ++n;
-        }
-    }
-    return d_back / (double)upsampling;                                              // :106
-}
-
-BAS_HD void bas_merge_term(BasTerm* out, int* n_out, long long* keys, double* wsum, int row, long long shift,
-                           double w, long long L) {
+BAS_HD int32_t bas_pack_term(int row, long long shift, long long L) {
     long long s = shift % L;
     if (s < 0) s += L;
-    const long long key = ((long long)row << 32) | s;
-    for (int i = 0; i < *n_out; ++i)
-        if (keys[i] == key) { wsum[i] += w; return; }
-    if (*n_out < BAS_MAX_TERMS) {
-        keys[*n_out] = key; wsum[*n_out] = w; ++*n_out;
-    }
-    (void)out;
+    return (int32_t)(((long long)row << 20) | s);
+}
+
+// out[0..n] = scale * in[0..n-1] * (p.c0 + p.c1 z)
+#define BAS_POLY_MUL(out, in, n, p)                                  \
+    do {                                                             \
+        (out)[0] = (in)[0] * (p).c0;                                 \
+        _Pragma("unroll") for (int i_ = 1; i_ < (n); ++i_)           \
+            (out)[i_] = (in)[i_] * (p).c0 + (in)[i_ - 1] * (p).c1;   \
+        (out)[n] = (in)[(n) - 1] * (p).c1;                           \
+    } while (0)
+
+struct BasRingEar {          // scalar results of one ring interpolation for one ear
+    BasDelay rem, res;       // remove (-d) and restore (alpha d) delays
+    double delay_out;        // alpha d / U, what the reference returns (apply_hrtf.py:106)
+};
+
+BAS_HD BasRingEar bas_ring_ear(const double* diffs, int upsampling, const BasRing& rg, int* err) {
+    BasRingEar r;
+    const double d = (double)upsampling * diffs[rg.before * BAS_N_DIR + rg.after];   // :82-83
+    r.rem = bas_split_delay(-d, err);                                                // :86-87
+    const double d_back = rg.alpha * d;                                              // :94-95
+    r.res = bas_split_delay(d_back, err);                                            // :98-102
+    r.delay_out = d_back / (double)upsampling;                                       // :106
+    return r;
 }
 
 // Ring mode: delay_compensated_interpolation_with_delaydiff (apply_hrtf.py:53-106) for one ear.
-// Writes up to BAS_MAX_TERMS merged terms and the reported delay.
 BAS_HD int bas_plan_ring_ear(const double* diffs, int upsampling, long long L, int before, int after,
                              double alpha, double one_minus_alpha, BasTerm* terms, double* delay_out,
                              long long* lo, long long* hi) {
     int err = 0;
     BasRing rg; rg.before = before; rg.after = after; rg.alpha = alpha; rg.one_minus_alpha = one_minus_alpha;
-    BasRawTerm raw[6];
-    *delay_out = bas_ring_terms(diffs, upsampling, rg, raw, lo, hi, &err);
-    long long keys[BAS_MAX_TERMS]; double wsum[BAS_MAX_TERMS]; int n = 0;
-    for (int i = 0; i < 6; ++i) bas_merge_term(terms, &n, keys, wsum, raw[i].row, raw[i].shift, raw[i].w, L);
-    for (int i = 0; i < BAS_MAX_TERMS; ++i) {
-        if (i < n) { terms[i].row_shift = (int32_t)(((keys[i] >> 32) << 20) | (keys[i] & 0xFFFFF)); terms[i].weight = (float)wsum[i]; }
-        else { terms[i].row_shift = 0; terms[i].weight = 0.0f; }
-    }
+    const BasRingEar re = bas_ring_ear(diffs, upsampling, rg, &err);
+    *delay_out = re.delay_out;
+    lo[0] = re.rem.lo; hi[0] = re.rem.hi; lo[1] = re.res.lo; hi[1] = re.res.hi;
+    const BasPoly2 p_res = bas_poly(re.res), p_rem = bas_poly(re.rem);
+    double wb[2] = {one_minus_alpha * p_res.c0, one_minus_alpha * p_res.c1};
+    double t1[2] = {alpha * p_res.c0, alpha * p_res.c1}, wa[3];
+    BAS_POLY_MUL(wa, t1, 2, p_rem);
+    for (int i = 0; i < BAS_MAX_TERMS; ++i) { terms[i].row_shift = 0; terms[i].weight = 0.0f; }
+    for (int i = 0; i < 2; ++i) { terms[i].row_shift = bas_pack_term(before, re.res.lo + i, L); terms[i].weight = (float)wb[i]; }
+    for (int i = 0; i < 3; ++i) { terms[2 + i].row_shift = bas_pack_term(after, re.res.lo + re.rem.lo + i, L); terms[2 + i].weight = (float)wa[i]; }
     return err;
 }
 
-// Full 2-D plan for one point: interpolate_2d (apply_hrtf.py:171-281).
-// diffs_l / diffs_r: 187x187 row-major doubles.  terms: [2][BAS_MAX_TERMS].  trace may be null.
-BAS_HD int bas_plan_point(const double* diffs_l, const double* diffs_r, int upsampling, long long L,
-                          double elev, double azim, int az_kind, BasTerm* terms, BasTrace* trace) {
-    int err = 0;
+struct BasPointGeom {        // the ear-independent part of a 2-D plan
+    BasRing top, bot;
+    double a;
+    int err;
+};
+
+// apply_hrtf.py:201-215, :261-266 and sphere.py:78-121
+BAS_HD BasPointGeom bas_point_geom(double elev, double azim, int az_kind) {
+    BasPointGeom g;
+    g.err = 0;
     // apply_hrtf.py:201-211: bracketing rings (comparisons in float64; NaN selects -45 / +90)
     int r_lo = -1, r_hi = -1;
     for (int r = 0; r < BAS_N_RING; ++r) {
@@ -217,52 +229,89 @@ BAS_HD int bas_plan_point(const double* diffs_l, const double* diffs_r, int upsa
     }
     if (r_lo < 0) r_lo = 0;
     if (r_hi < 0) r_hi = BAS_N_RING - 1;
-    BasRing top, bot;
-    top.before = top.after = bot.before = bot.after = 0; top.alpha = bot.alpha = 0.0;
-    top.one_minus_alpha = bot.one_minus_alpha = 1.0;
-    err |= bas_ring_lookup(r_hi, azim, az_kind, &top);             // :214
-    err |= bas_ring_lookup(r_lo, azim, az_kind, &bot);             // :215
-    double a = 0.0;                                                // :261-266
+    g.top.before = g.top.after = g.bot.before = g.bot.after = 0; g.top.alpha = g.bot.alpha = 0.0;
+    g.top.one_minus_alpha = g.bot.one_minus_alpha = 1.0;
+    g.err |= bas_ring_lookup(r_hi, azim, az_kind, &g.top);             // :214
+    g.err |= bas_ring_lookup(r_lo, azim, az_kind, &g.bot);             // :215
+    g.a = 0.0;                                                         // :261-266
     if (bas_ring_elev(r_hi) > bas_ring_elev(r_lo)) {
-        a = (elev - bas_ring_elev(r_lo)) / (bas_ring_elev(r_hi) - bas_ring_elev(r_lo));
-        if (!(0.0 <= a && a <= 1.0)) { err |= BAS_ERR_VERT_ASSERT; a = 0.0; }
+        g.a = (elev - bas_ring_elev(r_lo)) / (bas_ring_elev(r_hi) - bas_ring_elev(r_lo));
+        if (!(0.0 <= g.a && g.a <= 1.0)) { g.err |= BAS_ERR_VERT_ASSERT; g.a = 0.0; }
     }
+    return g;
+}
+
+// One ear of interpolate_2d (apply_hrtf.py:219-277): 16 terms, and the six floor/ceil pairs.
+BAS_HD int bas_plan_point_ear(const double* diffs, int upsampling, long long L, const BasPointGeom& g,
+                              BasTerm* out, long long* lo, long long* hi) {
+    int err = 0;
+    const BasRingEar rt = bas_ring_ear(diffs, upsampling, g.top, &err);                      // :219
+    const BasRingEar rb = bas_ring_ear(diffs, upsampling, g.bot, &err);                      // :220
+    // :246-252   U * (-delay_top + diffs[top_before, bot_before] + delay_bot)
+    const double dv = (double)upsampling * ((-rt.delay_out + diffs[g.top.before * BAS_N_DIR + g.bot.before]) + rb.delay_out);
+    const BasDelay vr = bas_split_delay(-dv, &err);                                         // :254-255
+    const double one_minus_a = 1.0 - g.a;
+    const BasDelay vs = bas_split_delay(one_minus_a * dv, &err);                            // :272-277
+    lo[0] = rt.rem.lo; hi[0] = rt.rem.hi; lo[1] = rt.res.lo; hi[1] = rt.res.hi;
+    lo[2] = rb.rem.lo; hi[2] = rb.rem.hi; lo[3] = rb.res.lo; hi[3] = rb.res.hi;
+    lo[4] = vr.lo; hi[4] = vr.hi; lo[5] = vs.lo; hi[5] = vs.hi;
+    const BasPoly2 p4 = bas_poly(vs), p3 = bas_poly(vr);
+    const BasPoly2 p2t = bas_poly(rt.res), p1t = bas_poly(rt.rem), p2b = bas_poly(rb.res), p1b = bas_poly(rb.rem);
+    // top: a * P4 * P2t * {(1-alpha_t), alpha_t * P1t}
+    double s1[1], s2[2], tb3[3], ta3[3], ta4[4];
+    s1[0] = g.a;
+    BAS_POLY_MUL(s2, s1, 1, p4);
+    double sb[2] = {s2[0] * g.top.one_minus_alpha, s2[1] * g.top.one_minus_alpha};
+    double sa[2] = {s2[0] * g.top.alpha, s2[1] * g.top.alpha};
+    BAS_POLY_MUL(tb3, sb, 2, p2t);
+    BAS_POLY_MUL(ta3, sa, 2, p2t);
+    BAS_POLY_MUL(ta4, ta3, 3, p1t);
+    // bottom: (1-a) * P4 * P3 * P2b * {(1-alpha_b), alpha_b * P1b}
+    double u1[1], u2[2], u3[3], bb4[4], ba4[4], ba5[5];
+    u1[0] = one_minus_a;
+    BAS_POLY_MUL(u2, u1, 1, p4);
+    BAS_POLY_MUL(u3, u2, 2, p3);
+    double ub[3] = {u3[0] * g.bot.one_minus_alpha, u3[1] * g.bot.one_minus_alpha, u3[2] * g.bot.one_minus_alpha};
+    double ua[3] = {u3[0] * g.bot.alpha, u3[1] * g.bot.alpha, u3[2] * g.bot.alpha};
+    BAS_POLY_MUL(bb4, ub, 3, p2b);
+    BAS_POLY_MUL(ba4, ua, 3, p2b);
+    BAS_POLY_MUL(ba5, ba4, 4, p1b);
+    const long long base_tb = vs.lo + rt.res.lo, base_ta = base_tb + rt.rem.lo;
+    const long long base_bb = vs.lo + vr.lo + rb.res.lo, base_ba = base_bb + rb.rem.lo;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 3; ++i) { out[i].row_shift = bas_pack_term(g.top.before, base_tb + i, L); out[i].weight = (float)tb3[i]; }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 4; ++i) { out[3 + i].row_shift = bas_pack_term(g.top.after, base_ta + i, L); out[3 + i].weight = (float)ta4[i]; }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 4; ++i) { out[7 + i].row_shift = bas_pack_term(g.bot.before, base_bb + i, L); out[7 + i].weight = (float)bb4[i]; }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 5; ++i) { out[11 + i].row_shift = bas_pack_term(g.bot.after, base_ba + i, L); out[11 + i].weight = (float)ba5[i]; }
+    return err;
+}
+
+// Full 2-D plan for one point: interpolate_2d (apply_hrtf.py:171-281), both ears (host path).
+// diffs_l / diffs_r: 187x187 row-major doubles.  terms: [2][BAS_MAX_TERMS].  trace may be null.
+BAS_HD int bas_plan_point(const double* diffs_l, const double* diffs_r, int upsampling, long long L,
+                          double elev, double azim, int az_kind, BasTerm* terms, BasTrace* trace) {
+    const BasPointGeom g = bas_point_geom(elev, azim, az_kind);
+    int err = g.err;
     if (trace) {
-        trace->rows[0] = top.before; trace->rows[1] = top.after;
-        trace->rows[2] = bot.before; trace->rows[3] = bot.after;
-        trace->alpha_top = top.alpha; trace->alpha_bot = bot.alpha; trace->a = a; trace->pad = 0;
+        trace->rows[0] = g.top.before; trace->rows[1] = g.top.after;
+        trace->rows[2] = g.bot.before; trace->rows[3] = g.bot.after;
+        trace->alpha_top = g.top.alpha; trace->alpha_bot = g.bot.alpha; trace->a = g.a; trace->pad = 0;
     }
     for (int e = 0; e < 2; ++e) {
-        const double* diffs = e ? diffs_r : diffs_l;
-        BasRawTerm tt[6], bt[6];
         long long lo[6], hi[6];
-        const double d_top = bas_ring_terms(diffs, upsampling, top, tt, lo + 0, hi + 0, &err);   // :219
-        const double d_bot = bas_ring_terms(diffs, upsampling, bot, bt, lo + 2, hi + 2, &err);   // :220
-        // :246-252   U * (-delay_top + diffs[top_before, bot_before] + delay_bot)
-        const double dv = (double)upsampling * ((-d_top + diffs[top.before * BAS_N_DIR + bot.before]) + d_bot);
-        const BasDelay vr = bas_split_delay(-dv, &err);                         // :254-255
-        const double one_minus_a = 1.0 - a;
-        const BasDelay vs = bas_split_delay(one_minus_a * dv, &err);            // :272-277
-        lo[4] = vr.lo; hi[4] = vr.hi; lo[5] = vs.lo; hi[5] = vs.hi;
+        err |= bas_plan_point_ear(e ? diffs_r : diffs_l, upsampling, L, g, terms + e * BAS_MAX_TERMS, lo, hi);
         if (trace) for (int i = 0; i < 6; ++i) { trace->lo[e][i] = lo[i]; trace->hi[e][i] = hi[i]; }
-        long long keys[BAS_MAX_TERMS]; double wsum[BAS_MAX_TERMS]; int n = 0;
-        const double w4[2] = {1.0 - vs.frac, vs.frac};
-        const long long s4[2] = {vs.lo, vs.hi};
-        const double w3[2] = {1.0 - vr.frac, vr.frac};
-        const long long s3[2] = {vr.lo, vr.hi};
-        for (int i = 0; i < 2; ++i) {
-            for (int k = 0; k < 6; ++k)                                          // a * hrtf_top   (:268-269)
-                bas_merge_term(0, &n, keys, wsum, tt[k].row, s4[i] + tt[k].shift, w4[i] * (a * tt[k].w), L);
-            for (int j = 0; j < 2; ++j)
-                for (int k = 0; k < 6; ++k)                                      // (1-a) * bottom_nodelay
-                    bas_merge_term(0, &n, keys, wsum, bt[k].row, s4[i] + s3[j] + bt[k].shift,
-                                   w4[i] * (one_minus_a * (w3[j] * bt[k].w)), L);
-        }
-        BasTerm* out = terms + e * BAS_MAX_TERMS;
-        for (int i = 0; i < BAS_MAX_TERMS; ++i) {
-            if (i < n) { out[i].row_shift = (int32_t)(((keys[i] >> 32) << 20) | (keys[i] & 0xFFFFF)); out[i].weight = (float)wsum[i]; }
-            else { out[i].row_shift = 0; out[i].weight = 0.0f; }
-        }
     }
     if (trace) trace->err = err;
     return err;
