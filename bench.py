@@ -213,13 +213,14 @@ def run_ours(args, rank, local_rank, world):
             x=x, elev=torch.from_numpy(np.ascontiguousarray(elev)).to(dev), azim=torch.from_numpy(np.ascontiguousarray(azim)).to(dev),
             terms=torch.empty(n_pts * 256, dtype=torch.uint8, device=dev), status=torch.zeros(2, dtype=torch.int32, device=dev),
             filt=torch.empty((n_pts, pitch, 2), dtype=torch.float32, device=dev),
-            out=torch.empty((2, n_out + 1), dtype=torch.float32, device=dev), peak=torch.zeros(1, dtype=torch.float32, device=dev)))
-    out_stride = n_out + 1
+            out=torch.empty((2, (n_out + 4) // 4 * 4), dtype=torch.float32, device=dev), peak=torch.zeros(1, dtype=torch.float32, device=dev)))
+    out_stride = (n_out + 4) // 4 * 4
+    workspace = _cabi.render_workspace(torch, dev)
 
     def step_render(s):
         _cabi.check(lib.bas_render(s['x'].data_ptr(), n_in, n_in, 1, n_in, CHUNK, SUB, k, s['filt'].data_ptr(), None,
-                                   0, n_out, s['out'].data_ptr(), out_stride, 0, s['peak'].data_ptr(), args.variant, stream),
-                    'bas_render')
+                                   0, n_out, s['out'].data_ptr(), out_stride, 0, s['peak'].data_ptr(), args.variant,
+                                   workspace.data_ptr(), workspace.numel(), stream), 'bas_render')
 
     def step(s):
         _cabi.check(lib.bas_plan_build(bdev.diffs[0].data_ptr(), bdev.diffs[1].data_ptr(), UPS, k * UPS, s['elev'].data_ptr(),

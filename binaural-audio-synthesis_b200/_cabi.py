@@ -18,6 +18,7 @@ AZ_PYFLOAT, AZ_F64, AZ_F32 = 0, 1, 2
 ERR_AZIM_ASSERT, ERR_VERT_ASSERT, ERR_NONFINITE = 1, 2, 4
 E_ARG, E_UNSUPPORTED, E_NO_DEVICE = -1, -2, -3
 RENDER_AUTO, RENDER_GENERIC, RENDER_TILED = 0, 1, 2
+RENDER_NO_SPLIT = 0x80
 IR_UPSAMPLED, IR_PLANAR, IR_ROWS = 0, 1, 2
 
 
@@ -58,7 +59,8 @@ def _load():
         'bas_plan_ring_host': ([vp, vp, i, i, i, i, C.c_double, C.c_double, vp, vp, vp, vp], i),
         'bas_ir_synth': ([vp, i, i, vp, ll, i, vp, ll, vp], i),
         'bas_filter_row_pitch': ([i], i),
-        'bas_render': ([vp, ll, ll, i, ll, i, i, i, vp, vp, ll, ll, vp, ll, i, vp, i, vp], i),
+        'bas_render': ([vp, ll, ll, i, ll, i, i, i, vp, vp, ll, ll, vp, ll, i, vp, i, vp, ll, vp], i),
+        'bas_render_workspace_bytes': ([], ll),
         'bas_normalise': ([vp, ll, vp, vp], i),
         'bas_peak': ([vp, ll, vp, vp], i),
         'bas_probe_fma': ([i, i, i, i, vp, vp], i),
@@ -85,6 +87,18 @@ def check(rc: int, what: str) -> None:
     """Raise on a non-zero status from a launch-type entry point."""
     if rc != 0:
         raise BasError('%s failed (status %d): %s' % (what, rc, last_error()))
+
+
+_workspaces = {}
+
+
+def render_workspace(torch, device):
+    """Per-device scratch for bas_render's tile splitting (allocated once, ~19 MB)."""
+    ws = _workspaces.get(device.index)
+    if ws is None:
+        ws = torch.empty(int(lib.bas_render_workspace_bytes()), dtype=torch.uint8, device=device)
+        _workspaces[device.index] = ws
+    return ws
 
 
 def require_device():

@@ -385,12 +385,13 @@ def render_sources(signals, chunksize: int, subchunksize: int, elev_azim_functio
     out = torch.empty((1 if mix else n_src, 2, stride), dtype=torch.float32, device=device)
     peaks = torch.zeros(n_src, dtype=torch.float32, device=device)
     stream = _stream(torch)
+    workspace = _cabi.render_workspace(torch, device)
 
     def launch(gains):
         _cabi.check(lib.bas_render(x.data_ptr(), n_in, n_in, n_src, n_in, chunksize, subchunksize, k,
                                    filt.data_ptr(), gains.data_ptr() if gains is not None else None,
                                    p0, count, out.data_ptr(), stride, 1 if mix else 0, peaks.data_ptr(), variant,
-                                   stream), 'bas_render')
+                                   workspace.data_ptr(), workspace.numel(), stream), 'bas_render')
 
     launch(None)
     if normalise and not mix:

@@ -43,11 +43,69 @@ bas_probe_fma_kernel(int iters, float* __restrict__ sink) {
     }
 }
 
+// FIR-shaped register streams: 32 (packed) or 64 (scalar) accumulators, a 32-entry ring of taps and a
+// fresh x scalar every 32 FMAs - the operand pattern of the render kernel without its loads.
+// mode 2: fma.rn.f32x2 acc[r] += {x,x} * w[(r-m)&31];   mode 3: the same arithmetic as scalar fma.rn.f32.
+template <int MODE>
+__global__ void __launch_bounds__(128)
+bas_probe_fir_kernel(int iters, float* __restrict__ sink) {
+    const float seed = (float)(threadIdx.x & 7) * 1e-3f;
+    float s = 0.f;
+    if (MODE == 2) {
+        unsigned long long acc[32], w[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            asm("mov.b64 %0, {%1, %2};" : "=l"(acc[i]) : "f"(seed + i), "f"(seed - i));
+            asm("mov.b64 %0, {%1, %2};" : "=l"(w[i]) : "f"(1e-3f * i + seed), "f"(2e-3f * i));
+        }
+        float x = 0.5f + seed;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int m = 0; m < 32; ++m) {
+                unsigned long long xx;
+                asm volatile("mov.b64 %0, {%1, %1};" : "=l"(xx) : "f"(x));
+#pragma unroll
+                for (int r = 0; r < 32; ++r)
+                    asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[r]) : "l"(xx), "l"(w[(r - m) & 31]));
+                x = x * 0.999f + 1e-4f;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[i])); s += lo + hi; }
+    } else {
+        float accl[32], accr[32], wl[32], wr[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { accl[i] = seed + i; accr[i] = seed - i; wl[i] = 1e-3f * i + seed; wr[i] = 2e-3f * i; }
+        float x = 0.5f + seed;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int m = 0; m < 32; ++m) {
+#pragma unroll
+                for (int r = 0; r < 32; ++r) {
+                    asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(accl[r]) : "f"(x), "f"(wl[(r - m) & 31]));
+                    asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(accr[r]) : "f"(x), "f"(wr[(r - m) & 31]));
+                }
+                x = x * 0.999f + 1e-4f;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) s += accl[i] + accr[i];
+    }
+    sink[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace
 
 extern "C" int bas_probe_fma(int packed, int blocks, int threads, int iters, float* sink_dev, void* stream) {
     BAS_CHECK_ARG(sink_dev, "null pointer");
     BAS_CHECK_ARG(blocks >= 1 && threads >= 32 && threads <= 256 && threads % 32 == 0 && iters >= 1, "launch shape");
+    if (packed == 2 || packed == 3) {       // FIR-shaped streams: FMA count = blocks * threads * iters * 2048
+        BAS_CHECK_ARG(threads <= 128, "FIR probes use at most 128 threads per block");
+        if (packed == 2) bas_probe_fir_kernel<2><<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, sink_dev);
+        else bas_probe_fir_kernel<3><<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, sink_dev);
+        BAS_LAUNCH_CHECK();
+        return 0;
+    }
     if (packed) bas_probe_fma_kernel<true><<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, sink_dev);
     else bas_probe_fma_kernel<false><<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, sink_dev);
     BAS_LAUNCH_CHECK();

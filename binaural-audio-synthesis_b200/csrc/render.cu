@@ -178,7 +178,8 @@ struct TileGeom {
     int D;              // tap blocks per tile: ceil(K / 32)
     int x_rows;         // 32-sample input rows of a tile
     int f_rows;         // filter rows staged per tile (chunks touched + 1)
-    unsigned x_bytes, f_bytes, stage_bytes;
+    int w_rows;         // input rows one warp reads (its 32 blocks + D)
+    unsigned x_bytes, f_bytes, stage_bytes, warp_x_bytes;
 };
 
 __host__ __device__ inline TileGeom tile_geom(int K, int C, int pitch, int TW) {
@@ -186,10 +187,15 @@ __host__ __device__ inline TileGeom tile_geom(int K, int C, int pitch, int TW) {
     g.D = (K + kBlk - 1) / kBlk;
     g.x_rows = TW * 32 + g.D;
     g.f_rows = (g.x_rows * kBlk + C - 1) / C + 2;
-    g.x_bytes = (unsigned)g.x_rows * kXPitch * 4;
+    g.w_rows = 32 + g.D;
+    g.x_bytes = (unsigned)g.x_rows * kBlk * 4;            // staged linearly (one bulk copy)
     g.f_bytes = (unsigned)g.f_rows * pitch * 8;
     g.stage_bytes = g.x_bytes + g.f_bytes;
+    g.warp_x_bytes = (unsigned)g.w_rows * kXPitch * 4;    // per-warp copy on the conflict-free pitch
     return g;
+}
+__host__ __device__ inline size_t tile_smem_bytes(const TileGeom& g, int TW) {
+    return 64 + (size_t)kStages * g.stage_bytes + (size_t)TW * g.warp_x_bytes;
 }
 constexpr size_t kBarBytes = 64;         // 2 x full + 2 x empty mbarriers, padded
 
@@ -238,9 +244,33 @@ __device__ __forceinline__ void block_32x32(u64 (&acc)[kBlk], const float2* __re
     }
 }
 
+// ---- work decomposition (stream-K) -----------------------------------------------------------------
+// The work of a launch is a line of SLICES grouped into GROUPS of gs slices that share one output
+// tile:   one source per tile (MIX = false): group = (source, tile), slice = tap block d, gs = D
+//         mixing                (MIX = true): group = tile,           slice = source,      gs = n_src
+// CTA c owns the contiguous slice span [c*total/G, (c+1)*total/G).  A span boundary that falls
+// inside a group splits that group between exactly two CTAs (spans are longer than a group); both
+// write their partial tile to the workspace and bas_render_fixup_kernel adds the two in a fixed order,
+// so results stay deterministic while every scheduler gets the same number of 32x32 blocks.  Without
+// a workspace spans are rounded to group boundaries.
+struct SpanInfo { long long total, n_groups; int gs; int split; };
+
+__host__ __device__ inline long long span_begin(const SpanInfo& sp, long long c, long long G) {
+    if (sp.split) return (long long)(((unsigned long long)c * (unsigned long long)sp.total) / (unsigned long long)G);
+    return (long long)(((unsigned long long)c * (unsigned long long)sp.n_groups) / (unsigned long long)G) * sp.gs;
+}
+
+struct Item {
+    long long tile; int src;
+    int d0, d1;             // tap blocks to run
+    bool group_end;         // outputs of the group are complete (for this CTA) after this item
+    bool partial;           // this CTA holds only part of the group -> workspace
+    int slot;               // workspace slot: 0 = group began in the previous CTA, 1 = continues in the next
+};
+
 template <int TW, bool MIX>
 __global__ void __launch_bounds__(TW * 32, 1)
-bas_render_tiled_kernel(RenderParams prm) {
+bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ workspace) {
     extern __shared__ __align__(128) unsigned char smem[];
     const TileGeom g = tile_geom(prm.K, prm.C, prm.pitch, TW);
     u64* full_bar = reinterpret_cast<u64*>(smem);              // [kStages]
@@ -248,13 +278,13 @@ bas_render_tiled_kernel(RenderParams prm) {
     unsigned char* stage_base = smem + kBarBytes;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* xw = reinterpret_cast<float*>(stage_base + (size_t)kStages * g.stage_bytes + (size_t)warp * g.warp_x_bytes);
     const long long p_base = prm.p_begin / kBlk * kBlk;
     const int spc = prm.C / kBlk;                              // subchunks per chunk
     const long long n_chunks = prm.n_in / prm.C;
-    const int ipu = MIX ? prm.n_src : 1;                       // pipeline items per unit of work
-    const long long n_units = MIX ? prm.tiles : prm.tiles * prm.n_src;
-    const long long my_units = blockIdx.x < n_units ? (n_units - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const long long n_items = my_units * ipu;
+    const long long i0 = span_begin(sp, blockIdx.x, gridDim.x), i1 = span_begin(sp, blockIdx.x + 1, gridDim.x);
+    const long long g_first = i0 / sp.gs;
+    const long long n_items = i1 <= i0 ? 0 : (MIX ? i1 - i0 : (i1 - 1) / sp.gs - g_first + 1);
 
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, TW); }
@@ -262,13 +292,26 @@ bas_render_tiled_kernel(RenderParams prm) {
     }
     __syncthreads();
 
-    // item j of this CTA -> (tile, source)
-    auto item_unit = [&](long long j, long long& tile, int& src) {
-        const long long unit = blockIdx.x + (j / ipu) * gridDim.x;
-        if (MIX) { tile = unit; src = (int)(j % ipu); }
-        else { src = (int)(unit / prm.tiles); tile = unit - (long long)src * prm.tiles; }
+    // item j of this CTA
+    auto item_info = [&](long long j) {
+        Item it;
+        const long long grp = MIX ? (i0 + j) / sp.gs : g_first + j;
+        const long long lo = grp * sp.gs;
+        const int a = (int)((i0 > lo ? i0 : lo) - lo), b = (int)((i1 < lo + sp.gs ? i1 : lo + sp.gs) - lo);
+        it.partial = a > 0 || b < sp.gs;
+        it.slot = a > 0 ? 0 : 1;
+        if (MIX) {
+            it.tile = grp; it.src = (int)(i0 + j - lo);
+            it.d0 = 0; it.d1 = g.D;
+            it.group_end = it.src == b - 1;
+        } else {
+            it.src = (int)(grp / prm.tiles); it.tile = grp - (long long)it.src * prm.tiles;
+            it.d0 = a; it.d1 = b;
+            it.group_end = true;
+        }
+        return it;
     };
-    // chunk range whose filter rows item needs (clamped to the signal)
+    // chunk range whose filter rows a tile needs (clamped to the signal)
     auto tile_chunks = [&](long long tile, long long& n_lo, long long& c_first, int& n_rows) {
         const long long P0 = p_base + tile * (TW * kWarpTile);
         n_lo = P0 - (long long)kBlk * g.D;
@@ -284,36 +327,25 @@ bas_render_tiled_kernel(RenderParams prm) {
         const int st = (int)(j % kStages);
         const long long use = j / kStages;
         if (use > 0) mbar_wait(empty_bar + st, (unsigned)((use - 1) & 1));      // consumers left the slot
-        long long tile, n_lo, c_first; int src, n_rows;
-        item_unit(j, tile, src);
-        tile_chunks(tile, n_lo, c_first, n_rows);
+        const Item it = item_info(j);
+        long long n_lo, c_first; int n_rows;
+        tile_chunks(it.tile, n_lo, c_first, n_rows);
         float* xs = reinterpret_cast<float*>(stage_base + (size_t)st * g.stage_bytes);
         float2* fs = reinterpret_cast<float2*>(stage_base + (size_t)st * g.stage_bytes + g.x_bytes);
-        const float* x = prm.x + (long long)src * prm.x_stride;
-        // rows that are not entirely inside [0, n_valid) are written by hand (zeros outside)
-        unsigned bytes = 0;
-        for (int row = lane; row < g.x_rows; row += 32) {
-            const long long n = n_lo + (long long)row * kBlk;
-            if (n >= 0 && n + kBlk <= prm.n_valid) {
-                bytes += kBlk * 4;
-            } else {
-                float* d = xs + row * kXPitch;
-#pragma unroll 4
-                for (int i = 0; i < kBlk; ++i) d[i] = (n + i >= 0 && n + i < prm.n_valid) ? x[n + i] : 0.f;
-            }
-        }
-        bytes = __reduce_add_sync(0xffffffffu, bytes);
-        __syncwarp();                                                          // hand-written rows ordered before the arrive
-        const unsigned f_bytes = (unsigned)n_rows * prm.pitch * 8;
+        const float* x = prm.x + (long long)it.src * prm.x_stride;
         if (lane == 0) {
-            mbar_arrive_expect_tx(full_bar + st, bytes + f_bytes);             // releases the hand-written rows too
-            bulk_g2s(fs, prm.filt + (long long)src * prm.filt_src_stride + c_first * prm.pitch, f_bytes, full_bar + st);
+            // two bulk copies per item: the in-range part of the input span, and the filter rows.
+            // Samples outside [0, n_valid) are never copied; consumers zero them while re-laying out.
+            const long long na = n_lo < 0 ? 0 : n_lo;
+            long long nb = n_lo + (long long)g.x_rows * kBlk;
+            if (nb > prm.n_valid) nb = prm.n_valid;
+            const unsigned x_bytes = nb > na ? (unsigned)(nb - na) * 4 : 0;
+            const unsigned f_bytes = (unsigned)n_rows * prm.pitch * 8;
+            mbar_arrive_expect_tx(full_bar + st, x_bytes + f_bytes);
+            if (x_bytes) bulk_g2s(xs + (na - n_lo), x + na, x_bytes, full_bar + st);
+            bulk_g2s(fs, prm.filt + (long long)it.src * prm.filt_src_stride + c_first * prm.pitch, f_bytes, full_bar + st);
         }
         __syncwarp();
-        for (int row = lane; row < g.x_rows; row += 32) {
-            const long long n = n_lo + (long long)row * kBlk;
-            if (n >= 0 && n + kBlk <= prm.n_valid) bulk_g2s(xs + row * kXPitch, x + n, kBlk * 4, full_bar + st);
-        }
     };
 
     if (warp == 0 && n_items > 0) produce(0);
@@ -333,10 +365,10 @@ bas_render_tiled_kernel(RenderParams prm) {
     for (long long j = 0; j < n_items; ++j) {
         if (warp == 0 && j + 1 < n_items) produce(j + 1);
         const int st = (int)(j % kStages);
-        long long tile, n_lo, c_first; int src, n_rows;
-        item_unit(j, tile, src);
-        tile_chunks(tile, n_lo, c_first, n_rows);
-        const long long P0 = p_base + tile * (TW * kWarpTile);
+        const Item it = item_info(j);
+        long long n_lo, c_first; int n_rows;
+        tile_chunks(it.tile, n_lo, c_first, n_rows);
+        const long long P0 = p_base + it.tile * (TW * kWarpTile);
         const bool warp_live = P0 + (long long)warp * kWarpTile < prm.p_end;
         const float* xs = reinterpret_cast<const float*>(stage_base + (size_t)st * g.stage_bytes);
         const float2* fs = reinterpret_cast<const float2*>(stage_base + (size_t)st * g.stage_bytes + g.x_bytes);
@@ -345,34 +377,59 @@ bas_render_tiled_kernel(RenderParams prm) {
         mbar_wait(full_bar + st, (unsigned)((j / kStages) & 1));
 
         if (warp_live) {
-            // per-lane filter row pointer and blend weight of input row `xrow`
-            auto lane_filter = [&](int xrow, const float2*& rowp, u64& alpha2) {
-                const long long q = q0 + xrow;
-                long long chunk = q < 0 ? 0 : q / spc;
-                const int sub = q < 0 ? 0 : (int)(q - chunk * spc);
-                long long ri = chunk - c_first;                  // rows outside the staged range belong
-                if (ri < 0) ri = 0;                              // to input rows that are all zero
-                if (ri > n_rows - 2) ri = n_rows - 2;
-                const float alpha = (float)(sub * kBlk) / (float)prm.C;          // apply_hrtf.py:442
+            // re-lay this warp's input rows from the linear staging buffer onto the 144-byte pitch
+            // (lane-per-row reads below are then conflict free) and zero what lies outside the signal
+            const long long n_w = n_lo + (long long)warp * kWarpTile;
+            const float4* lin = reinterpret_cast<const float4*>(xs) + warp * (kWarpTile / 4);
+            for (int idx = lane; idx < g.w_rows * 8; idx += 32) {
+                const int row = idx >> 3, ch = idx & 7;
+                const long long n = n_w + (long long)row * kBlk + ch * 4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (n >= 0 && n + 4 <= prm.n_valid) v = lin[idx];
+                *reinterpret_cast<float4*>(xw + row * kXPitch + ch * 4) = v;
+            }
+            __syncwarp();
+        }
+        if (warp_live) {
+            // Filter row (chunk) and blend weight of the lane's input row.  Input rows are visited in
+            // descending order (xrow = blk + D - d), so (chunk, sub) is divided once per item and then
+            // stepped; rows outside the staged range belong to input rows that are all zero (clamped).
+            const int q_top = (int)q0 + blk + g.D;               // absolute subchunk of the d = 0 row
+            const int cf = (int)c_first;
+            int chunk_a = q_top < 0 ? 0 : q_top / spc;
+            int sub_a = q_top < 0 ? 0 : q_top - chunk_a * spc;
+            auto row_of = [&](int chunk, const float2*& rowp) {
+                int ri = chunk - cf;
+                ri = ri < 0 ? 0 : (ri > n_rows - 2 ? n_rows - 2 : ri);
                 rowp = fs + ri * prm.pitch;
-                alpha2 = pack2(alpha, alpha);
             };
             // d = 0 is the folded block: ring initialised from the d = 0 filter (r >= m), refilled from
             // the d = D filter (r < m).  One call site keeps the unrolled body in the instruction cache.
 #pragma unroll 1
-            for (int d = 0; d < g.D; ++d) {
-                const float2 *ra, *rb; u64 aa, ab;
+            for (int d = it.d0; d < it.d1; ++d) {
+                // (chunk, sub) of row q_top - d
+                int chunk = chunk_a, sub = sub_a - d;
+                if (q_top - d < 0) { chunk = 0; sub = 0; }
+                else { while (sub < 0) { sub += spc; --chunk; } }
+                const float2 *ra, *rb;
+                row_of(chunk, ra);
+                ra += kBlk * d;
+                const float alpha = (float)(sub * kBlk) / (float)prm.C;          // apply_hrtf.py:442
+                u64 aa = pack2(alpha, alpha), ab = aa;
+                rb = ra;
                 const int xrow_a = blk + g.D - d;
                 int xrow_b = xrow_a;
-                lane_filter(xrow_a, ra, aa);
-                ra += kBlk * d;
-                rb = ra; ab = aa;
                 if (d == 0) {
                     xrow_b = blk;
-                    lane_filter(xrow_b, rb, ab);
+                    const int qb = q_top - g.D;
+                    const int chunk_b = qb < 0 ? 0 : qb / spc;
+                    const int sub_b = qb < 0 ? 0 : qb - chunk_b * spc;
+                    row_of(chunk_b, rb);
                     rb += kBlk * g.D;
+                    const float alpha_b = (float)(sub_b * kBlk) / (float)prm.C;
+                    ab = pack2(alpha_b, alpha_b);
                 }
-                block_32x32(acc, ra, aa, rb, ab, prm.pitch, xs + xrow_a * kXPitch, xs + xrow_b * kXPitch);
+                block_32x32(acc, ra, aa, rb, ab, prm.pitch, xw + (xrow_a - warp * 32) * kXPitch, xw + (xrow_b - warp * 32) * kXPitch);
             }
         }
         __syncwarp();
@@ -380,8 +437,8 @@ bas_render_tiled_kernel(RenderParams prm) {
 
         // ---- peak, gain, mix, store ----------------------------------------------------------------
         const long long pb = P0 + (long long)blk * kBlk;        // first output of this lane
-        const float gain = prm.gains ? prm.gains[src] : 1.f;
-        if (prm.peaks) {
+        const float gain = prm.gains ? prm.gains[it.src] : 1.f;
+        if (prm.peaks && (MIX || !it.partial)) {                // split tiles get their peak in the fix-up
             float pk = 0.f;
 #pragma unroll
             for (int r = 0; r < kBlk; ++r) {
@@ -389,36 +446,47 @@ bas_render_tiled_kernel(RenderParams prm) {
                 if (pb + r >= prm.p_begin && pb + r < prm.p_end) pk = fmaxf(pk, fmaxf(fabsf(l), fabsf(rr)));
             }
             pk = warp_max(pk);
-            if (lane == 0 && pk > 0.f) atomic_max_nonneg(prm.peaks + src, pk);
+            if (lane == 0 && pk > 0.f) atomic_max_nonneg(prm.peaks + it.src, pk);
         }
-        bool store = true;
         if (MIX) {
             const u64 g2 = pack2(gain, gain);
 #pragma unroll
             for (int r = 0; r < kBlk; ++r) { mixacc[r & (MIX ? 31 : 0)] = fma2(g2, acc[r], mixacc[r & (MIX ? 31 : 0)]); acc[r] = 0ull; }
-            store = (j % ipu) == ipu - 1;
         }
-        if (store) {
-            float* o = prm.out + (MIX ? 0 : (long long)src * 2 * prm.out_stride);
-            const long long off = pb - prm.p_begin;
-            if (vec_ok && pb >= prm.p_begin && pb + kBlk <= prm.p_end) {
+        if (it.group_end) {
+            if (it.partial) {
+                // partial tile -> workspace[cta][slot][ear][TW*1024], no gain (one source per tile) / mixed
+                float* w = workspace + ((long long)blockIdx.x * 2 + it.slot) * (2 * TW * kWarpTile) + blk * kBlk;
 #pragma unroll
                 for (int r4 = 0; r4 < kBlk; r4 += 4) {
                     float l[4], rr[4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        unpack2(MIX ? mixacc[(r4 + i) & (MIX ? 31 : 0)] : acc[r4 + i], l[i], rr[i]);
-                        if (!MIX) { l[i] *= gain; rr[i] *= gain; }
-                    }
-                    *reinterpret_cast<float4*>(o + off + r4) = make_float4(l[0], l[1], l[2], l[3]);
-                    *reinterpret_cast<float4*>(o + prm.out_stride + off + r4) = make_float4(rr[0], rr[1], rr[2], rr[3]);
+                    for (int i = 0; i < 4; ++i) unpack2(MIX ? mixacc[(r4 + i) & (MIX ? 31 : 0)] : acc[r4 + i], l[i], rr[i]);
+                    *reinterpret_cast<float4*>(w + r4) = make_float4(l[0], l[1], l[2], l[3]);
+                    *reinterpret_cast<float4*>(w + TW * kWarpTile + r4) = make_float4(rr[0], rr[1], rr[2], rr[3]);
                 }
             } else {
+                float* o = prm.out + (MIX ? 0 : (long long)it.src * 2 * prm.out_stride);
+                const long long off = pb - prm.p_begin;
+                if (vec_ok && pb >= prm.p_begin && pb + kBlk <= prm.p_end) {
 #pragma unroll
-                for (int r = 0; r < kBlk; ++r) {
-                    float l, rr; unpack2(MIX ? mixacc[r & (MIX ? 31 : 0)] : acc[r], l, rr);
-                    if (!MIX) { l *= gain; rr *= gain; }
-                    if (pb + r >= prm.p_begin && pb + r < prm.p_end) { o[off + r] = l; o[prm.out_stride + off + r] = rr; }
+                    for (int r4 = 0; r4 < kBlk; r4 += 4) {
+                        float l[4], rr[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            unpack2(MIX ? mixacc[(r4 + i) & (MIX ? 31 : 0)] : acc[r4 + i], l[i], rr[i]);
+                            if (!MIX) { l[i] *= gain; rr[i] *= gain; }
+                        }
+                        *reinterpret_cast<float4*>(o + off + r4) = make_float4(l[0], l[1], l[2], l[3]);
+                        *reinterpret_cast<float4*>(o + prm.out_stride + off + r4) = make_float4(rr[0], rr[1], rr[2], rr[3]);
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < kBlk; ++r) {
+                        float l, rr; unpack2(MIX ? mixacc[r & (MIX ? 31 : 0)] : acc[r], l, rr);
+                        if (!MIX) { l *= gain; rr *= gain; }
+                        if (pb + r >= prm.p_begin && pb + r < prm.p_end) { o[off + r] = l; o[prm.out_stride + off + r] = rr; }
+                    }
                 }
             }
 #pragma unroll
@@ -431,32 +499,85 @@ bas_render_tiled_kernel(RenderParams prm) {
     }
 }
 
-template <int TW, bool MIX>
-int launch_tiled(RenderParams prm, cudaStream_t st) {
-    const TileGeom g = tile_geom(prm.K, prm.C, prm.pitch, TW);
-    const size_t smem = kBarBytes + (size_t)kStages * g.stage_bytes;
-    if (smem > 227 * 1024) return BAS_E_UNSUPPORTED;
-    auto kern = bas_render_tiled_kernel<TW, MIX>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { bas_set_error("bas_render: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+// Adds the two partial tiles of every group a span boundary split (fixed order: the earlier CTA's
+// part first), applies the gain, takes the peak and stores.  grid = (boundaries, 2 ears, T / 1024).
+__global__ void __launch_bounds__(256)
+bas_render_fixup_kernel(RenderParams prm, SpanInfo sp, const float* __restrict__ workspace, long long G, int TW) {
+    const long long c = blockIdx.x + 1;                           // boundary between CTA c-1 and CTA c
+    const int ear = blockIdx.y;
+    const long long ic = span_begin(sp, c, G);
+    if (ic % sp.gs == 0 || ic >= sp.total) return;                // boundary on a group edge: nothing was split
+    const long long grp = ic / sp.gs;
+    const int T = TW * kWarpTile;
+    const int src = prm.mix ? 0 : (int)(grp / prm.tiles);
+    const long long tile = prm.mix ? grp : grp - (long long)src * prm.tiles;
     const long long p_base = prm.p_begin / kBlk * kBlk;
-    prm.tiles = bas_ceil_div(prm.p_end - p_base, (long long)TW * kWarpTile);
-    const long long units = prm.mix ? prm.tiles : prm.tiles * prm.n_src;
-    // persistent grid: as many CTAs as the device keeps resident
+    const int i = blockIdx.z * kWarpTile + threadIdx.x * 4;       // 256 threads x 4 outputs
+    const long long p = p_base + tile * T + i;
+    const float4 a = *reinterpret_cast<const float4*>(workspace + ((c - 1) * 2 + 1) * (2LL * T) + (long long)ear * T + i);
+    const float4 b = *reinterpret_cast<const float4*>(workspace + (c * 2 + 0) * (2LL * T) + (long long)ear * T + i);
+    const float gain = (!prm.mix && prm.gains) ? prm.gains[src] : 1.f;
+    float* o = prm.out + (prm.mix ? 0 : (long long)src * 2 * prm.out_stride) + (long long)ear * prm.out_stride;
+    const float v[4] = {a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w};
+    float pk = 0.f;
+    const bool vec_ok = (prm.p_begin & 3) == 0 && (prm.out_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(prm.out) & 15) == 0;
+    if (vec_ok && p >= prm.p_begin && p + 4 <= prm.p_end) {
+        pk = fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3])));
+        *reinterpret_cast<float4*>(o + (p - prm.p_begin)) = make_float4(gain * v[0], gain * v[1], gain * v[2], gain * v[3]);
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (p + e >= prm.p_begin && p + e < prm.p_end) { pk = fmaxf(pk, fabsf(v[e])); o[p + e - prm.p_begin] = gain * v[e]; }
+    }
+    if (prm.peaks && !prm.mix) {
+        pk = warp_max(pk);
+        if ((threadIdx.x & 31) == 0 && pk > 0.f) atomic_max_nonneg(prm.peaks + src, pk);
+    }
+}
+
+int device_sm_count() {
     static thread_local int sm_count = 0;
     if (!sm_count) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
     }
+    return sm_count;
+}
+
+template <int TW, bool MIX>
+int launch_tiled(RenderParams prm, float* workspace, long long workspace_bytes, cudaStream_t st) {
+    const TileGeom g = tile_geom(prm.K, prm.C, prm.pitch, TW);
+    const size_t smem = tile_smem_bytes(g, TW);
+    if (smem > 227 * 1024) return BAS_E_UNSUPPORTED;
+    auto kern = bas_render_tiled_kernel<TW, MIX>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { bas_set_error("bas_render: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    const long long p_base = prm.p_begin / kBlk * kBlk;
+    prm.tiles = bas_ceil_div(prm.p_end - p_base, (long long)TW * kWarpTile);
+    SpanInfo sp;
+    sp.gs = MIX ? prm.n_src : g.D;
+    sp.n_groups = MIX ? prm.tiles : prm.tiles * prm.n_src;
+    sp.total = sp.n_groups * sp.gs;
+    // persistent grid: as many CTAs as the device keeps resident
     int per_sm = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TW * 32, smem);
     if (e != cudaSuccess || per_sm < 1) { bas_set_error("bas_render: tile shape does not fit an SM"); cudaGetLastError(); return BAS_E_UNSUPPORTED; }
-    long long grid = (long long)sm_count * per_sm;
-    if (grid > units) grid = units;
-    kern<<<(unsigned)grid, TW * 32, smem, st>>>(prm);
+    long long grid = (long long)device_sm_count() * per_sm;
+    if (grid > sp.n_groups) grid = sp.n_groups;
+    // split groups between CTAs only when every span is longer than a group (then a group has at
+    // most two contributors) and the caller gave a workspace
+    const long long need = grid * 2 * (2LL * TW * kWarpTile) * 4;
+    sp.split = (workspace && workspace_bytes >= need && grid > 1 && sp.total / grid >= sp.gs + 1) ? 1 : 0;
+    kern<<<(unsigned)grid, TW * 32, smem, st>>>(prm, sp, workspace);
     e = cudaGetLastError();
     if (e != cudaSuccess) { bas_set_error("bas_render: tiled launch failed: %s", cudaGetErrorString(e)); return (int)e; }
+    if (sp.split) {
+        dim3 fgrid((unsigned)(grid - 1), 2, (unsigned)TW);
+        bas_render_fixup_kernel<<<fgrid, 256, 0, st>>>(prm, sp, workspace, grid, TW);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) { bas_set_error("bas_render: fix-up launch failed: %s", cudaGetErrorString(e)); return (int)e; }
+    }
     return 0;
 }
 
@@ -487,7 +608,7 @@ bas_normalise_kernel(float* __restrict__ v, long long n, const float* __restrict
 extern "C" int bas_render(const float* x_dev, long long x_stride, long long n_valid, int n_src, long long n_in,
                           int C, int S, int K, const float* filt_dev, const float* gains_dev,
                           long long p_begin, long long p_count, float* out_dev, long long out_stride, int mix,
-                          float* peaks_dev, int variant, void* stream) {
+                          float* peaks_dev, int variant, void* workspace_dev, long long workspace_bytes, void* stream) {
     BAS_CHECK_ARG(x_dev && filt_dev && out_dev, "null pointer");
     BAS_CHECK_ARG(n_src >= 1, "n_src");
     BAS_CHECK_ARG(C >= 1 && S >= 1 && C % S == 0, "subchunksize must divide chunksize");     // apply_hrtf.py:401-402
@@ -496,6 +617,7 @@ extern "C" int bas_render(const float* x_dev, long long x_stride, long long n_va
     BAS_CHECK_ARG(n_valid >= 0 && n_valid <= n_in && (n_src == 1 || x_stride >= n_valid), "n_valid / x_stride");
     BAS_CHECK_ARG(p_begin >= 0 && p_count >= 0 && p_begin + p_count <= n_in + K - 1, "output range");
     BAS_CHECK_ARG(out_stride >= p_count, "out_stride < p_count");
+    BAS_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace_dev) & 15) == 0 && workspace_bytes >= 0, "workspace");
     if (p_count == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     RenderParams prm;
@@ -506,12 +628,12 @@ extern "C" int bas_render(const float* x_dev, long long x_stride, long long n_va
     prm.gains = gains_dev; prm.p_begin = p_begin; prm.p_end = p_begin + p_count;
     prm.out = out_dev; prm.out_stride = out_stride; prm.mix = mix ? 1 : 0; prm.peaks = peaks_dev; prm.tiles = 0;
 
-    const int base = variant & 0xff;
+    const int base = variant & 0x7f;
     BAS_CHECK_ARG(base == BAS_RENDER_AUTO || base == BAS_RENDER_GENERIC || base == BAS_RENDER_TILED, "variant");
-    const bool tiled_ok = S == kBlk && C % kBlk == 0 && (reinterpret_cast<uintptr_t>(x_dev) & 15) == 0 &&
+    const bool tiled_ok = S == kBlk && C % kBlk == 0 && n_valid % 4 == 0 && (reinterpret_cast<uintptr_t>(x_dev) & 15) == 0 &&
                           (reinterpret_cast<uintptr_t>(filt_dev) & 15) == 0 && (n_src == 1 || x_stride % 4 == 0);
     if (base == BAS_RENDER_TILED && !tiled_ok) {
-        bas_set_error("bas_render: tiled kernel needs S == 32, 32 | C, 16-byte aligned signals and filter rows");
+        bas_set_error("bas_render: tiled kernel needs S == 32, 32 | C, 4 | n_valid, 16-byte aligned signals and filter rows");
         return BAS_E_UNSUPPORTED;
     }
     if (base != BAS_RENDER_GENERIC && tiled_ok) {
@@ -521,10 +643,11 @@ extern "C" int bas_render(const float* x_dev, long long x_stride, long long n_va
         const int order[3] = {tw_req ? tw_req : 4, tw_req ? 0 : 2, tw_req ? 0 : 1};
         for (int i = 0; i < 3 && rc == BAS_E_UNSUPPORTED; ++i) {
             const int tw = order[i];
-            if (tw == 8) rc = prm.mix ? launch_tiled<8, true>(prm, st) : launch_tiled<8, false>(prm, st);
-            else if (tw == 4) rc = prm.mix ? launch_tiled<4, true>(prm, st) : launch_tiled<4, false>(prm, st);
-            else if (tw == 2) rc = prm.mix ? launch_tiled<2, true>(prm, st) : launch_tiled<2, false>(prm, st);
-            else if (tw == 1) rc = prm.mix ? launch_tiled<1, true>(prm, st) : launch_tiled<1, false>(prm, st);
+            float* ws = (variant & BAS_RENDER_NO_SPLIT) ? nullptr : reinterpret_cast<float*>(workspace_dev);
+            if (tw == 8) rc = prm.mix ? launch_tiled<8, true>(prm, ws, workspace_bytes, st) : launch_tiled<8, false>(prm, ws, workspace_bytes, st);
+            else if (tw == 4) rc = prm.mix ? launch_tiled<4, true>(prm, ws, workspace_bytes, st) : launch_tiled<4, false>(prm, ws, workspace_bytes, st);
+            else if (tw == 2) rc = prm.mix ? launch_tiled<2, true>(prm, ws, workspace_bytes, st) : launch_tiled<2, false>(prm, ws, workspace_bytes, st);
+            else if (tw == 1) rc = prm.mix ? launch_tiled<1, true>(prm, ws, workspace_bytes, st) : launch_tiled<1, false>(prm, ws, workspace_bytes, st);
         }
         if (rc != BAS_E_UNSUPPORTED || base == BAS_RENDER_TILED) {
             if (rc == BAS_E_UNSUPPORTED) bas_set_error("bas_render: no tile shape fits K=%d C=%d (requested TW=%d)", K, C, tw_req);
@@ -538,6 +661,11 @@ extern "C" int bas_render(const float* x_dev, long long x_stride, long long n_va
     bas_render_generic_kernel<<<grid, threads, 0, st>>>(prm);
     BAS_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" long long bas_render_workspace_bytes(void) {
+    // resident warps x 2 slots x (1024 outputs x 2 ears) floats, whatever the tile shape
+    return (long long)device_sm_count() * 8 * 2 * (2LL * kWarpTile) * 4;
 }
 
 extern "C" int bas_peak(const float* v_dev, long long n, float* peak_dev, void* stream) {

@@ -129,14 +129,21 @@ int bas_filter_row_pitch(int K);
  * peaks_dev: n_src floats, max |out| of each source over the rendered range BEFORE gain and mixing
  *            (for apply_hrtf.py:462), or NULL.  Must be zeroed by the caller (atomic max).
  * variant:   BAS_RENDER_AUTO / _GENERIC (any C, S, K) / _TILED (needs S == 32, C % 32 == 0,
- *            16-byte aligned signals; BAS_E_UNSUPPORTED otherwise). */
+ *            16-byte aligned signals; BAS_E_UNSUPPORTED otherwise).
+ * workspace_dev / workspace_bytes: see bas_render_workspace_bytes (16-byte aligned, or NULL). */
 #define BAS_RENDER_AUTO 0
 #define BAS_RENDER_GENERIC 1
 #define BAS_RENDER_TILED 2
+#define BAS_RENDER_NO_SPLIT 0x80    /* OR-ed into variant: never split a tile between CTAs */
 int bas_render(const float* x_dev, long long x_stride, long long n_valid, int n_src, long long n_in,
                int C, int S, int K, const float* filt_dev, const float* gains_dev,
                long long p_begin, long long p_count, float* out_dev, long long out_stride, int mix,
-               float* peaks_dev, int variant, void* stream);
+               float* peaks_dev, int variant, void* workspace_dev, long long workspace_bytes, void* stream);
+
+/* Scratch the tiled renderer may use to balance work across SMs (a tile split between two CTAs is
+ * summed there in a fixed order, so results stay deterministic).  workspace_dev may be NULL: tiles
+ * are then never split.  Contents need no initialisation and carry nothing between calls. */
+long long bas_render_workspace_bytes(void);
 
 /* apply_hrtf.py:462-464: divide n floats by *peak_dev when it exceeds 1 (no-op otherwise). */
 int bas_normalise(float* out_dev, long long n, const float* peak_dev, void* stream);

@@ -27,7 +27,7 @@ def test_header_symbols_exported(bas):
     """Every function include/bas_b200.h declares is exported by the library."""
     import os
     header = open(os.path.join(os.path.dirname(bas._cabi._HERE), 'include', 'bas_b200.h')).read()
-    declared = set(re.findall(r'^int (bas_\w+)\(', header, flags=re.M))
+    declared = set(re.findall(r'^(?:int|long long) (bas_\w+)\(', header, flags=re.M))
     assert len(declared) >= 13
     lib = C.CDLL(bas._cabi.LIB_PATH)
     for name in declared:

@@ -22,7 +22,8 @@ def main():
     n_src = int(sys.argv[1]) if len(sys.argv) > 1 else 1
     keep = int(sys.argv[2]) if len(sys.argv) > 2 else 256
     ups = int(sys.argv[3]) if len(sys.argv) > 3 else 8
-    mix = 1 if n_src > 1 else 0
+    mix = int(sys.argv[4]) if len(sys.argv) > 4 else (1 if n_src > 1 else 0)
+    only_tw = int(sys.argv[5]) if len(sys.argv) > 5 else 0
     dev = torch.device('cuda', 0)
     f = bas.bank_synth.build_bank(ups, seed=0)
 
@@ -31,27 +32,30 @@ def main():
         diffs_left, diffs_right = f['diffs_left'], f['diffs_right']
         irs_left, irs_right = f['irs_left'][:, :keep * ups], f['irs_right'][:, :keep * ups]
     bdev = bas.apply_hrtf._device_bank(bank)
-    n = 60 * 44100
+    seconds = float(os.environ.get('BAS_SECONDS', '60'))
+    n = int(seconds * 44100)
     k, n_in, n_out = bas.render_geometry(n, 512, 32, bank)
     n_pts = n_in // 512 + 1
     stream = torch.cuda.current_stream().cuda_stream
     x = (0.05 * torch.randn((n_src, n_in), device=dev)).contiguous()
     pitch = lib.bas_filter_row_pitch(k)
     filt = (0.05 * torch.randn((n_src, n_pts, pitch, 2), device=dev)).contiguous()
-    out = torch.empty((1 if mix else n_src, 2, n_out + 1), device=dev)
+    out = torch.empty((1 if mix else n_src, 2, (n_out + 4) // 4 * 4), device=dev)
     peaks = torch.zeros(n_src, device=dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
     results = {}
-    for tw in (1, 2, 4, 8):
-        ts = 1
-        variant = _cabi.RENDER_TILED | (tw << 8)
+    workspace = _cabi.render_workspace(torch, dev)
+    for tw, ts in ((1, 0), (2, 0), (4, 0), (8, 0), (2, 1), (4, 1)):
+        if only_tw and (tw != only_tw or ts):
+            continue
+        variant = _cabi.RENDER_TILED | (tw << 8) | (_cabi.RENDER_NO_SPLIT if ts else 0)
 
         def run():
             return lib.bas_render(x.data_ptr(), n_in, n_in, n_src, n_in, 512, 32, k, filt.data_ptr(), None, 0, n_out,
-                                  out.data_ptr(), n_out + 1, mix, peaks.data_ptr(), variant, stream)
+                                  out.data_ptr(), out.shape[-1], mix, peaks.data_ptr(), variant, workspace.data_ptr(), workspace.numel(), stream)
         rc = run()
         if rc != 0:
-            results['%dx%d' % (tw, ts)] = 'rc=%d %s' % (rc, _cabi.last_error())
+            results['%dx%s' % (tw, 'nosplit' if ts else 'split')] = 'rc=%d %s' % (rc, _cabi.last_error())
             continue
         torch.cuda.synchronize()
         times = []
@@ -64,9 +68,9 @@ def main():
             torch.cuda.synchronize()
             times.append(e0.elapsed_time(e1))
         ms = float(np.median(times))
-        results['%dx%d' % (tw, ts)] = {'ms': round(ms, 4), 'tfma_s': round(2.0 * k * n_in * n_src / ms / 1e9, 2),
+        results['%dx%s' % (tw, 'nosplit' if ts else 'split')] = {'ms': round(ms, 4), 'tfma_s': round(2.0 * k * n_in * n_src / ms / 1e9, 2),
                                         'Gpairs_s': round(n_out * n_src / ms / 1e6, 2)}
-    print(json.dumps({'n_src': n_src, 'K': k, 'U': ups, 'results': results}, indent=1))
+    print(json.dumps({'seconds': seconds, 'mix': mix, 'n_src': n_src, 'K': k, 'U': ups, 'results': results}, indent=1))
 
 
 if __name__ == '__main__':
