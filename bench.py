@@ -316,7 +316,8 @@ def run_ours(args, rank, local_rank, world):
         }
 
         # ---- e2e through the public API with host buffers ---------------------------------------
-        x_host = pink_noise(n, 2)
+        x_pinned = torch.from_numpy(pink_noise(n, 2)).pin_memory()      # e2e inputs live in pinned host memory
+        x_host = x_pinned.numpy()
         traj = lissajous(0)
         e2e_steps = max(3, min(args.steps, 20))
         for _ in range(2):

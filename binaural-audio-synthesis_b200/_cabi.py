@@ -18,7 +18,7 @@ AZ_PYFLOAT, AZ_F64, AZ_F32 = 0, 1, 2
 ERR_AZIM_ASSERT, ERR_VERT_ASSERT, ERR_NONFINITE = 1, 2, 4
 E_ARG, E_UNSUPPORTED, E_NO_DEVICE = -1, -2, -3
 RENDER_AUTO, RENDER_GENERIC, RENDER_TILED = 0, 1, 2
-RENDER_NO_SPLIT = 0x80
+RENDER_SPLIT, RENDER_NO_SPLIT = 0x40, 0x80
 IR_UPSAMPLED, IR_PLANAR, IR_ROWS = 0, 1, 2
 
 

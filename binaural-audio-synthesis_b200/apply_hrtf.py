@@ -344,19 +344,25 @@ def render_sources(signals, chunksize: int, subchunksize: int, elev_azim_functio
     torch = _cabi.require_device()
     dev = _device_bank(irs_and_delaydiffs)
     device = dev.device
+    # ---- signals -> HBM, zero padded to a multiple of chunksize (apply_hrtf.py:405-406) ----------
     if isinstance(signals, torch.Tensor):
-        x = signals.to(device=device, dtype=torch.float32)
+        src = signals
     else:
-        x = torch.from_numpy(np.ascontiguousarray(signals, dtype=np.float32)).to(device)
-    if x.dim() != 2:
+        src = torch.from_numpy(np.ascontiguousarray(signals, dtype=np.float32))
+    if src.dim() != 2:
         raise ValueError('signals must be (n_src, N)')
-    n_src, n = x.shape
+    n_src, n = src.shape
     k, n_in, n_out = render_geometry(n, chunksize, subchunksize, irs_and_delaydiffs)
     assert k == dev.taps
-    if n_in != n or not x.is_contiguous():
-        padded = torch.zeros((n_src, n_in), dtype=torch.float32, device=device)     # apply_hrtf.py:405-406
-        padded[:, :n] = x
-        x = padded
+    if src.is_cuda and src.dtype == torch.float32 and src.is_contiguous() and n == n_in and src.device == device:
+        x = src
+    else:
+        x = torch.empty((n_src, n_in), dtype=torch.float32, device=device)
+        if n_in > n:
+            x[:, n:].zero_()
+        # pinned host memory is copied by DMA without a staging pass; pageable memory goes through
+        # the driver's bounce buffers
+        x[:, :n].copy_(src, non_blocking=(not src.is_cuda) and src.is_pinned())
     n_pts = n_in // chunksize + 1
     times = range(0, n_in + 1, chunksize)
     if isinstance(elev_azim_functions, tuple) and len(elev_azim_functions) == 3 and not callable(elev_azim_functions[0]):
@@ -397,7 +403,20 @@ def render_sources(signals, chunksize: int, subchunksize: int, elev_azim_functio
     if normalise and not mix:
         for s in range(n_src):        # apply_hrtf.py:462-464 per source, peak read on the device
             _cabi.check(lib.bas_normalise(out[s].data_ptr(), 2 * stride, peaks[s:s + 1].data_ptr(), stream), 'bas_normalise')
-    host = torch.cat([status, peaks.view(torch.int32)]).cpu().numpy()   # one small sync: status + peaks
+    # ---- results back: status + peaks and (unless return_device) the audio, one synchronisation ----
+    small = torch.empty(2 + n_src, dtype=torch.int32, pin_memory=True)
+    small.copy_(torch.cat([status, peaks.view(torch.int32)]), non_blocking=True)
+    result = out[..., :count]
+    if mix:
+        result = result[0]
+    host_out = None
+    if not return_device:
+        # pinned destination from torch's caching host allocator: DMA straight into the array the
+        # caller receives (no pageable bounce, no extra host copy)
+        host_out = torch.empty(result.shape, dtype=torch.float32, pin_memory=True)
+        host_out.copy_(result, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    host = small.numpy()
     err, where = int(host[0]), int(host[1])
     if err:
         _raise_plan_error(err, ' (trajectory point %d of source %d)' % (where % n_pts, where // n_pts))
@@ -406,11 +425,11 @@ def render_sources(signals, chunksize: int, subchunksize: int, elev_azim_functio
         gains = torch.from_numpy((1.0 / np.maximum(peaks_host, 1.0)).astype(np.float32)).to(device)
         peaks.zero_()
         launch(gains)
-    result = out[..., :count]
-    if mix:
-        result = result[0]
-    if not return_device:
-        result = result.cpu().numpy()
+        if host_out is not None:
+            host_out.copy_(result, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+    if host_out is not None:
+        result = host_out.numpy()
     return (result, peaks_host) if return_peaks else result
 
 

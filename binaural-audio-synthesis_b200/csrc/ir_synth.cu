@@ -67,51 +67,66 @@ bas_ir_synth_kernel(const float* __restrict__ bank_pp, int U, int K, const BasTe
     }
 }
 
-// filter-row layout for the renderer: one CTA per point, both ears per thread, out[point][m][ear]
-// with taps K..pitch-1 zeroed (bas_filter_row_pitch).  Term tables of both ears are compacted first.
+// filter-row layout for the renderer: both ears per thread, out[point][m][ear] with taps K..pitch-1
+// zeroed (bas_filter_row_pitch).  A CTA walks over kPointsPerCta CONSECUTIVE trajectory points:
+// neighbouring points use the same bank rows and, delays moving by a fraction of a sample per chunk,
+// mostly the same phase rows, so their gathers hit in L1 instead of going back to L2.
+constexpr int kPointsPerCta = 1;
+
 __global__ void __launch_bounds__(kThreads)
-bas_ir_synth_rows_kernel(const float* __restrict__ bank_pp, int U, int K, int pitch,
+bas_ir_synth_rows_kernel(const float* __restrict__ bank_pp, int U, int K, int pitch, long long n_points,
                          const BasTermDev* __restrict__ terms, float2* __restrict__ out) {
-    const long long point = blockIdx.x;
     const int L = U * K;
-    __shared__ int s_base[2][kMaxTerms];
-    __shared__ int s_adv[2][kMaxTerms];
-    __shared__ float s_w[2][kMaxTerms];
-    __shared__ int s_n[2];
-    if (threadIdx.x < 64) {
-        const int ear = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        BasTermDev t; t.row_shift = 0; t.weight = 0.f;
-        if (lane < kMaxTerms) t = terms[(point * 2 + ear) * kMaxTerms + lane];
-        const bool live = t.weight != 0.f;
-        const unsigned mask = __ballot_sync(0xffffffffu, live);
-        if (live) {
-            const int slot = __popc(mask & ((1u << lane) - 1u));
-            const int row = t.row_shift >> 20, shift = t.row_shift & 0xFFFFF;
-            const int ph = (U - shift % U) % U;
-            s_base[ear][slot] = (ear * BAS_N_DIRECTIONS + row) * L + ph * K;
-            s_adv[ear][slot] = (shift + ph) / U;
-            s_w[ear][slot] = t.weight;
+    __shared__ int s_base[2][2][kMaxTerms];
+    __shared__ int s_adv[2][2][kMaxTerms];
+    __shared__ float s_w[2][2][kMaxTerms];
+    __shared__ int s_n[2][2];
+    const long long first = (long long)blockIdx.x * kPointsPerCta;
+    // warps 0 and 1 compact the non-zero terms of the two ears of point `pt` into buffer `buf`
+    auto load_terms = [&](long long pt, int buf) {
+        if (threadIdx.x < 64 && pt < n_points) {
+            const int ear = threadIdx.x >> 5, lane = threadIdx.x & 31;
+            BasTermDev t; t.row_shift = 0; t.weight = 0.f;
+            if (lane < kMaxTerms) t = terms[(pt * 2 + ear) * kMaxTerms + lane];
+            const bool live = t.weight != 0.f;
+            const unsigned mask = __ballot_sync(0xffffffffu, live);
+            if (live) {
+                const int slot = __popc(mask & ((1u << lane) - 1u));
+                const int row = t.row_shift >> 20, shift = t.row_shift & 0xFFFFF;
+                const int ph = (U - shift % U) % U;
+                s_base[buf][ear][slot] = (ear * BAS_N_DIRECTIONS + row) * L + ph * K;
+                s_adv[buf][ear][slot] = (shift + ph) / U;
+                s_w[buf][ear][slot] = t.weight;
+            }
+            if (lane == 0) s_n[buf][ear] = __popc(mask);
         }
-        if (lane == 0) s_n[ear] = __popc(mask);
-    }
+    };
+    load_terms(first, 0);
     __syncthreads();
-    const int n_l = s_n[0], n_r = s_n[1];
-    float2* dst = out + point * pitch;
-    for (int m = threadIdx.x; m < pitch; m += kThreads) {
-        float acc_l = 0.f, acc_r = 0.f;
-        if (m < K) {
-            for (int t = 0; t < n_l; ++t) {
-                int j = m - s_adv[0][t];
-                j += (j < 0) ? K : 0;
-                acc_l = fmaf(s_w[0][t], __ldg(bank_pp + s_base[0][t] + j), acc_l);
+    for (int i = 0; i < kPointsPerCta; ++i) {
+        const long long point = first + i;
+        if (point >= n_points) break;
+        const int buf = i & 1;
+        load_terms(point + 1 < first + kPointsPerCta ? point + 1 : n_points, buf ^ 1);   // prefetch the next table
+        const int n_l = s_n[buf][0], n_r = s_n[buf][1];
+        float2* dst = out + point * pitch;
+        for (int m = threadIdx.x; m < pitch; m += kThreads) {
+            float acc_l = 0.f, acc_r = 0.f;
+            if (m < K) {
+                for (int t = 0; t < n_l; ++t) {
+                    int j = m - s_adv[buf][0][t];
+                    j += (j < 0) ? K : 0;
+                    acc_l = fmaf(s_w[buf][0][t], __ldg(bank_pp + s_base[buf][0][t] + j), acc_l);
+                }
+                for (int t = 0; t < n_r; ++t) {
+                    int j = m - s_adv[buf][1][t];
+                    j += (j < 0) ? K : 0;
+                    acc_r = fmaf(s_w[buf][1][t], __ldg(bank_pp + s_base[buf][1][t] + j), acc_r);
+                }
             }
-            for (int t = 0; t < n_r; ++t) {
-                int j = m - s_adv[1][t];
-                j += (j < 0) ? K : 0;
-                acc_r = fmaf(s_w[1][t], __ldg(bank_pp + s_base[1][t] + j), acc_r);
-            }
+            dst[m] = make_float2(acc_l, acc_r);
         }
-        dst[m] = make_float2(acc_l, acc_r);
+        __syncthreads();
     }
 }
 
@@ -157,8 +172,8 @@ extern "C" int bas_ir_synth(const float* bank_pp_dev, int U, int K, const bas_te
     const BasTermDev* terms = reinterpret_cast<const BasTermDev*>(terms_dev);
     if (mode == BAS_IR_ROWS) {
         BAS_CHECK_ARG((reinterpret_cast<uintptr_t>(out_dev) & 15) == 0, "filter rows must be 16-byte aligned");
-        bas_ir_synth_rows_kernel<<<(unsigned)n_points, kThreads, 0, st>>>(bank_pp_dev, U, K, bas_filter_row_pitch(K), terms,
-                                                                         reinterpret_cast<float2*>(out_dev));
+        bas_ir_synth_rows_kernel<<<(unsigned)bas_ceil_div(n_points, kPointsPerCta), kThreads, 0, st>>>(
+            bank_pp_dev, U, K, bas_filter_row_pitch(K), n_points, terms, reinterpret_cast<float2*>(out_dev));
     } else if (mode == BAS_IR_PLANAR) {
         dim3 grid((unsigned)n_points, 2);
         bas_ir_synth_kernel<<<grid, kThreads, 0, st>>>(bank_pp_dev, U, K, terms, out_dev, out_stride);

@@ -282,9 +282,13 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
     const long long p_base = prm.p_begin / kBlk * kBlk;
     const int spc = prm.C / kBlk;                              // subchunks per chunk
     const long long n_chunks = prm.n_in / prm.C;
-    const long long i0 = span_begin(sp, blockIdx.x, gridDim.x), i1 = span_begin(sp, blockIdx.x + 1, gridDim.x);
+    // split: contiguous slice span [i0, i1);  otherwise whole groups, dealt round-robin (group = c + k G)
+    const long long i0 = sp.split ? span_begin(sp, blockIdx.x, gridDim.x) : 0;
+    const long long i1 = sp.split ? span_begin(sp, blockIdx.x + 1, gridDim.x) : 0;
     const long long g_first = i0 / sp.gs;
-    const long long n_items = i1 <= i0 ? 0 : (MIX ? i1 - i0 : (i1 - 1) / sp.gs - g_first + 1);
+    const long long my_groups = blockIdx.x < sp.n_groups ? (sp.n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long n_items = sp.split ? (i1 <= i0 ? 0 : (MIX ? i1 - i0 : (i1 - 1) / sp.gs - g_first + 1))
+                                       : my_groups * (MIX ? sp.gs : 1);
 
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, TW); }
@@ -295,13 +299,22 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
     // item j of this CTA
     auto item_info = [&](long long j) {
         Item it;
-        const long long grp = MIX ? (i0 + j) / sp.gs : g_first + j;
-        const long long lo = grp * sp.gs;
-        const int a = (int)((i0 > lo ? i0 : lo) - lo), b = (int)((i1 < lo + sp.gs ? i1 : lo + sp.gs) - lo);
+        long long grp; int a, b;
+        if (sp.split) {
+            grp = MIX ? (i0 + j) / sp.gs : g_first + j;
+            const long long lo = grp * sp.gs;
+            a = (int)((i0 > lo ? i0 : lo) - lo); b = (int)((i1 < lo + sp.gs ? i1 : lo + sp.gs) - lo);
+            it.src = MIX ? (int)(i0 + j - lo) : 0;
+        } else {
+            const long long k = MIX ? j / sp.gs : j;
+            grp = blockIdx.x + k * gridDim.x;
+            a = 0; b = sp.gs;
+            it.src = MIX ? (int)(j - k * sp.gs) : 0;
+        }
         it.partial = a > 0 || b < sp.gs;
         it.slot = a > 0 ? 0 : 1;
         if (MIX) {
-            it.tile = grp; it.src = (int)(i0 + j - lo);
+            it.tile = grp;
             it.d0 = 0; it.d1 = g.D;
             it.group_end = it.src == b - 1;
         } else {
@@ -546,7 +559,7 @@ int device_sm_count() {
 }
 
 template <int TW, bool MIX>
-int launch_tiled(RenderParams prm, float* workspace, long long workspace_bytes, cudaStream_t st) {
+int launch_tiled(RenderParams prm, bool want_split, float* workspace, long long workspace_bytes, cudaStream_t st) {
     const TileGeom g = tile_geom(prm.K, prm.C, prm.pitch, TW);
     const size_t smem = tile_smem_bytes(g, TW);
     if (smem > 227 * 1024) return BAS_E_UNSUPPORTED;
@@ -568,7 +581,7 @@ int launch_tiled(RenderParams prm, float* workspace, long long workspace_bytes, 
     // split groups between CTAs only when every span is longer than a group (then a group has at
     // most two contributors) and the caller gave a workspace
     const long long need = grid * 2 * (2LL * TW * kWarpTile) * 4;
-    sp.split = (workspace && workspace_bytes >= need && grid > 1 && sp.total / grid >= sp.gs + 1) ? 1 : 0;
+    sp.split = (want_split && workspace && workspace_bytes >= need && grid > 1 && sp.total / grid >= sp.gs + 1) ? 1 : 0;
     kern<<<(unsigned)grid, TW * 32, smem, st>>>(prm, sp, workspace);
     e = cudaGetLastError();
     if (e != cudaSuccess) { bas_set_error("bas_render: tiled launch failed: %s", cudaGetErrorString(e)); return (int)e; }
@@ -628,7 +641,7 @@ extern "C" int bas_render(const float* x_dev, long long x_stride, long long n_va
     prm.gains = gains_dev; prm.p_begin = p_begin; prm.p_end = p_begin + p_count;
     prm.out = out_dev; prm.out_stride = out_stride; prm.mix = mix ? 1 : 0; prm.peaks = peaks_dev; prm.tiles = 0;
 
-    const int base = variant & 0x7f;
+    const int base = variant & 0x3f;
     BAS_CHECK_ARG(base == BAS_RENDER_AUTO || base == BAS_RENDER_GENERIC || base == BAS_RENDER_TILED, "variant");
     const bool tiled_ok = S == kBlk && C % kBlk == 0 && n_valid % 4 == 0 && (reinterpret_cast<uintptr_t>(x_dev) & 15) == 0 &&
                           (reinterpret_cast<uintptr_t>(filt_dev) & 15) == 0 && (n_src == 1 || x_stride % 4 == 0);
@@ -640,14 +653,17 @@ extern "C" int bas_render(const float* x_dev, long long x_stride, long long n_va
         const int tw_req = (variant >> 8) & 0xff;
         int rc = BAS_E_UNSUPPORTED;
         // default: 4 warps per CTA, falling back to smaller tiles when shared memory runs out
-        const int order[3] = {tw_req ? tw_req : 4, tw_req ? 0 : 2, tw_req ? 0 : 1};
+        const int order[3] = {tw_req ? tw_req : (prm.mix ? 8 : 4), tw_req ? 0 : 2, tw_req ? 0 : 1};
         for (int i = 0; i < 3 && rc == BAS_E_UNSUPPORTED; ++i) {
             const int tw = order[i];
-            float* ws = (variant & BAS_RENDER_NO_SPLIT) ? nullptr : reinterpret_cast<float*>(workspace_dev);
-            if (tw == 8) rc = prm.mix ? launch_tiled<8, true>(prm, ws, workspace_bytes, st) : launch_tiled<8, false>(prm, ws, workspace_bytes, st);
-            else if (tw == 4) rc = prm.mix ? launch_tiled<4, true>(prm, ws, workspace_bytes, st) : launch_tiled<4, false>(prm, ws, workspace_bytes, st);
-            else if (tw == 2) rc = prm.mix ? launch_tiled<2, true>(prm, ws, workspace_bytes, st) : launch_tiled<2, false>(prm, ws, workspace_bytes, st);
-            else if (tw == 1) rc = prm.mix ? launch_tiled<1, true>(prm, ws, workspace_bytes, st) : launch_tiled<1, false>(prm, ws, workspace_bytes, st);
+            // Splitting tiles between CTAs pays when a tile carries many sources (mixing); with one
+            // source per tile whole tiles dealt round-robin measured faster (fewer, longer items).
+            float* ws = reinterpret_cast<float*>(workspace_dev);
+            const bool split = (variant & BAS_RENDER_SPLIT) || (prm.mix && !(variant & BAS_RENDER_NO_SPLIT));
+            if (tw == 8) rc = prm.mix ? launch_tiled<8, true>(prm, split, ws, workspace_bytes, st) : launch_tiled<8, false>(prm, split, ws, workspace_bytes, st);
+            else if (tw == 4) rc = prm.mix ? launch_tiled<4, true>(prm, split, ws, workspace_bytes, st) : launch_tiled<4, false>(prm, split, ws, workspace_bytes, st);
+            else if (tw == 2) rc = prm.mix ? launch_tiled<2, true>(prm, split, ws, workspace_bytes, st) : launch_tiled<2, false>(prm, split, ws, workspace_bytes, st);
+            else if (tw == 1) rc = prm.mix ? launch_tiled<1, true>(prm, split, ws, workspace_bytes, st) : launch_tiled<1, false>(prm, split, ws, workspace_bytes, st);
         }
         if (rc != BAS_E_UNSUPPORTED || base == BAS_RENDER_TILED) {
             if (rc == BAS_E_UNSUPPORTED) bas_set_error("bas_render: no tile shape fits K=%d C=%d (requested TW=%d)", K, C, tw_req);

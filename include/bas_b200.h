@@ -134,6 +134,7 @@ int bas_filter_row_pitch(int K);
 #define BAS_RENDER_AUTO 0
 #define BAS_RENDER_GENERIC 1
 #define BAS_RENDER_TILED 2
+#define BAS_RENDER_SPLIT 0x40       /* OR-ed into variant: always balance by splitting tiles between CTAs */
 #define BAS_RENDER_NO_SPLIT 0x80    /* OR-ed into variant: never split a tile between CTAs */
 int bas_render(const float* x_dev, long long x_stride, long long n_valid, int n_src, long long n_in,
                int C, int S, int K, const float* filt_dev, const float* gains_dev,

@@ -45,10 +45,10 @@ def main():
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
     results = {}
     workspace = _cabi.render_workspace(torch, dev)
-    for tw, ts in ((1, 0), (2, 0), (4, 0), (8, 0), (2, 1), (4, 1)):
+    for tw, ts in ((1, 0), (2, 0), (4, 0), (8, 0), (2, 1), (4, 1), (8, 1)):
         if only_tw and (tw != only_tw or ts):
             continue
-        variant = _cabi.RENDER_TILED | (tw << 8) | (_cabi.RENDER_NO_SPLIT if ts else 0)
+        variant = _cabi.RENDER_TILED | (tw << 8) | (_cabi.RENDER_NO_SPLIT if ts else _cabi.RENDER_SPLIT)
 
         def run():
             return lib.bas_render(x.data_ptr(), n_in, n_in, n_src, n_in, 512, 32, k, filt.data_ptr(), None, 0, n_out,
