@@ -318,7 +318,7 @@ def evaluate_trajectory(elev_azim_function, times):
     azim = np.empty(n, dtype=np.float64)
     kinds = np.empty(n, dtype=np.uint8)
     for i, t in enumerate(times):
-        e, a = elev_azim_function(t)
+        e, a = elev_azim_function(int(t))            # a Python int, like range() gives the reference
         elev[i] = e
         azim[i] = a
         kinds[i] = sphere.az_kind(a)
@@ -364,7 +364,7 @@ def render_sources(signals, chunksize: int, subchunksize: int, elev_azim_functio
         # the driver's bounce buffers
         x[:, :n].copy_(src, non_blocking=(not src.is_cuda) and src.is_pinned())
     n_pts = n_in // chunksize + 1
-    times = range(0, n_in + 1, chunksize)
+    times = np.arange(0, n_in + 1, chunksize, dtype=np.int64)
     if isinstance(elev_azim_functions, tuple) and len(elev_azim_functions) == 3 and not callable(elev_azim_functions[0]):
         elev, azim, kinds = elev_azim_functions
     else:

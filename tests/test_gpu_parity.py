@@ -117,15 +117,27 @@ def _traj(seed, fs=44100.0):
     return fn
 
 
-@pytest.mark.parametrize('tw', [1, 2, 4, 8])
-def test_tiled_shapes_vs_oracle(bas, oracle, synth_bank, tw):
-    """Every compiled tile shape (warps per CTA) of the register-tiled kernel, K = 256."""
+_SHAPE_REF = {}
+
+
+def _shape_reference(oracle, bank, x, traj):
+    if 'y' not in _SHAPE_REF:
+        _SHAPE_REF['y'] = oracle.make_signal_move_2d(x, 512, 32, traj, bank)
+    return _SHAPE_REF['y']
+
+
+@pytest.mark.parametrize('split', [False, True])
+@pytest.mark.parametrize('ns', [1, 2])
+@pytest.mark.parametrize('tw', [2, 4, 8])
+def test_tiled_shapes_vs_oracle(bas, oracle, synth_bank, tw, ns, split):
+    """Every compiled tile shape (warps per CTA x pipeline stages) of the register-tiled kernel,
+    with whole tiles per CTA and with tiles split between CTAs (stream-K + fix-up), K = 256."""
     rng = np.random.default_rng(5)
     n = 9000
     x = (0.05 * rng.standard_normal(n)).astype(np.float32)
     traj = _traj(3)
-    want = oracle.make_signal_move_2d(x, 512, 32, traj, synth_bank)
-    variant = bas._cabi.RENDER_TILED | (tw << 8)
+    want = _shape_reference(oracle, synth_bank, x, traj)
+    variant = bas._cabi.RENDER_TILED | (tw << 8) | (ns << 16) | (bas._cabi.RENDER_SPLIT if split else bas._cabi.RENDER_NO_SPLIT)
     got = bas.render_sources(x[None], 512, 32, [traj], synth_bank, variant=variant)[0].T
     close(got, want)
 

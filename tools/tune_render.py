@@ -45,17 +45,17 @@ def main():
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
     results = {}
     workspace = _cabi.render_workspace(torch, dev)
-    for tw, ts in ((1, 0), (2, 0), (4, 0), (8, 0), (2, 1), (4, 1), (8, 1)):
+    for tw, ns, ts in ((0, 0, 0), (0, 0, 1), (2, 2, 0), (4, 2, 0), (8, 2, 0), (2, 2, 1), (4, 2, 1), (8, 2, 1), (4, 1, 1), (8, 1, 1), (8, 1, 0)):
         if only_tw and (tw != only_tw or ts):
             continue
-        variant = _cabi.RENDER_TILED | (tw << 8) | (_cabi.RENDER_NO_SPLIT if ts else _cabi.RENDER_SPLIT)
+        variant = _cabi.RENDER_TILED | (tw << 8) | (ns << 16) | (_cabi.RENDER_NO_SPLIT if ts else _cabi.RENDER_SPLIT)
 
         def run():
             return lib.bas_render(x.data_ptr(), n_in, n_in, n_src, n_in, 512, 32, k, filt.data_ptr(), None, 0, n_out,
                                   out.data_ptr(), out.shape[-1], mix, peaks.data_ptr(), variant, workspace.data_ptr(), workspace.numel(), stream)
         rc = run()
         if rc != 0:
-            results['%dx%s' % (tw, 'nosplit' if ts else 'split')] = 'rc=%d %s' % (rc, _cabi.last_error())
+            results['%dx%d%s' % (tw, ns, 'nosplit' if ts else 'split')] = 'rc=%d %s' % (rc, _cabi.last_error())
             continue
         torch.cuda.synchronize()
         times = []
@@ -68,7 +68,7 @@ def main():
             torch.cuda.synchronize()
             times.append(e0.elapsed_time(e1))
         ms = float(np.median(times))
-        results['%dx%s' % (tw, 'nosplit' if ts else 'split')] = {'ms': round(ms, 4), 'tfma_s': round(2.0 * k * n_in * n_src / ms / 1e9, 2),
+        results['%dx%d%s' % (tw, ns, 'nosplit' if ts else 'split')] = {'ms': round(ms, 4), 'tfma_s': round(2.0 * k * n_in * n_src / ms / 1e9, 2),
                                         'Gpairs_s': round(n_out * n_src / ms / 1e6, 2)}
     print(json.dumps({'seconds': seconds, 'mix': mix, 'n_src': n_src, 'K': k, 'U': ups, 'results': results}, indent=1))
 
