@@ -315,25 +315,33 @@ def run_ours(args, rank, local_rank, world):
             'ir_synth_ms_per_launch': ms_synth, 'plan_build_ms_per_launch': ms_plan,
         }
 
-        # ---- e2e through the public API with host buffers ---------------------------------------
-        x_pinned = torch.from_numpy(pink_noise(n, 2)).pin_memory()      # e2e inputs live in pinned host memory
-        x_host = x_pinned.numpy()
-        traj = lissajous(0)
-        e2e_steps = max(3, min(args.steps, 20))
-        for _ in range(2):
-            bas.make_signal_move_2d(x_host, CHUNK, SUB, traj, bank)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            y = bas.make_signal_move_2d(x_host, CHUNK, SUB, traj, bank)
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / e2e_steps
-        line['e2e'] = {'value': n_out / dt, 'unit': UNIT, 'h2d_bytes_per_step': int(4 * n + 16 * n_pts),
-                       'd2h_bytes_per_step': int(8 * n_out + 12), 'ms_per_step': 1e3 * dt, 'steps': e2e_steps,
-                       'call': 'make_signal_move_2d(host float32 ndarray, 512, 32, vectorised trajectory, bank) -> host ndarray',
-                       'n_gpus': 1}
-        assert y.shape == (n_out, 2)
+    # ---- e2e through the public API with host buffers, on every rank (its own source, its own PCIe
+    #      link): pinned host signal in, host array out, copies inside the timed region -------------
+    x_pinned = torch.from_numpy(pink_noise(n, 2 + 100 * rank)).pin_memory()      # e2e inputs live in pinned host memory
+    x_host = x_pinned.numpy()
+    traj = lissajous(0 if rank == 0 else 1 + 100 * rank)
+    e2e_steps = max(3, min(args.steps, 50))
+    y = None
+    for _ in range(max(warmup, 4)):        # results are held like in the timed loop: two pinned result buffers alternate
+        y = bas.make_signal_move_2d(x_host, CHUNK, SUB, traj, bank)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        y = bas.make_signal_move_2d(x_host, CHUNK, SUB, traj, bank)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / e2e_steps
+    assert y.shape == (n_out, 2)
+    if dist is not None:
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t)
+    line['e2e'] = {'value': world * n_out / dt, 'unit': UNIT, 'h2d_bytes_per_step': int(4 * n + 16 * n_pts),
+                   'd2h_bytes_per_step': int(8 * n_out + 12), 'ms_per_step': 1e3 * dt, 'steps': e2e_steps,
+                   'call': 'make_signal_move_2d(host float32 ndarray, 512, 32, vectorised trajectory, bank) -> host ndarray, '
+                           'one call per rank per step, wall clock, max over ranks',
+                   'n_gpus': world}
 
+    if rank == 0:
         # ---- CPU baseline: numpy port of the reference, one core, first seconds of the workload ----
         if world == 1 and not args.no_cpu:
             from oracle import binaural_oracle as oracle
@@ -341,15 +349,13 @@ def run_ours(args, rank, local_rank, world):
             sample_s = 4
             xs = x_host[:sample_s * FS]
             t0 = time.perf_counter()
-            yo = oracle.make_signal_move_2d(xs, CHUNK, SUB, lambda t: traj(np.float64(t)), obank)
+            yo = oracle.make_signal_move_2d(xs, CHUNK, SUB, lambda t: traj(np.float64(t)), obank)   # rank 0: traj = lissajous(0)
             dt = time.perf_counter() - t0
             line['cpu_baseline'] = {'value': yo.shape[0] / dt, 'unit': UNIT, 'cores': 1, 'kind': 'port',
                                     'sample': 'first %d s of the workload signal, single process (numpy oracle port)' % sample_s}
             got = y[:xs.size - 1000].astype(np.float64)
             err = np.linalg.norm(got - yo[:xs.size - 1000]) / np.linalg.norm(yo[:xs.size - 1000])
             line['cpu_baseline']['gpu_vs_port_rel_l2'] = float(err)
-    if world > 1 and rank == 0:
-        pass
     if world > 1:
         # the config-3 exchange step, reported beside the data path: SUM-reduce of one (2, N_out) mix
         mix = sets[0]['out']

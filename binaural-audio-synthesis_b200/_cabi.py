@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libbas_b200.so')
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 N_DIRECTIONS = 187
 MAX_TERMS = 16
 AZ_PYFLOAT, AZ_F64, AZ_F32 = 0, 1, 2
@@ -35,6 +35,20 @@ class Trace(C.Structure):
 TRACE_DTYPE = [('rows', '<i4', (4,)), ('err', '<i4'), ('pad', '<i4'), ('alpha_top', '<f8'),
                ('alpha_bot', '<f8'), ('a', '<f8'), ('lo', '<i8', (2, 6)), ('hi', '<i8', (2, 6))]
 TERM_DTYPE = [('row_shift', '<i4'), ('weight', '<f4')]
+
+
+class PipelineJob(C.Structure):
+    """bas_pipeline_job (include/bas_b200.h)."""
+    _fields_ = [('n_src', C.c_int), ('C', C.c_int), ('S', C.c_int), ('K', C.c_int), ('U', C.c_int), ('mix', C.c_int),
+                ('variant', C.c_int), ('az_kind_all', C.c_int),
+                ('n', C.c_longlong), ('n_in', C.c_longlong), ('p_begin', C.c_longlong), ('p_count', C.c_longlong),
+                ('x_host_stride', C.c_longlong), ('segment_bytes', C.c_longlong),
+                ('x_host', C.c_void_p), ('x_dev', C.c_void_p), ('dirs_host', C.c_void_p), ('az_kind_host', C.c_void_p),
+                ('diffs_left_dev', C.c_void_p), ('diffs_right_dev', C.c_void_p), ('bank_pp_dev', C.c_void_p),
+                ('out_host', C.c_void_p), ('small_host', C.c_void_p),
+                ('arena_dev', C.c_void_p), ('arena_bytes', C.c_longlong),
+                ('workspace_dev', C.c_void_p), ('workspace_bytes', C.c_longlong),
+                ('stream_main', C.c_void_p), ('stream_up', C.c_void_p), ('stream_down', C.c_void_p)]
 
 
 class BasError(RuntimeError):
@@ -63,6 +77,11 @@ def _load():
         'bas_render_workspace_bytes': ([], ll),
         'bas_normalise': ([vp, ll, vp, vp], i),
         'bas_peak': ([vp, ll, vp, vp], i),
+        'bas_copy_2d': ([vp, ll, vp, ll, ll, ll, i, vp], i),
+        'bas_pipeline_arena_bytes': ([i, ll, i, i, i, ll, i, C.POINTER(ll)], ll),
+        'bas_pipeline_upload': ([C.POINTER(PipelineJob), i, C.POINTER(ll)], i),
+        'bas_pipeline_phase': ([C.POINTER(PipelineJob), i, i, ll, ll, ll, ll], i),
+        'bas_pipeline_trace': ([i, C.c_char_p, C.c_size_t], i),
         'bas_probe_fma': ([i, i, i, i, vp, vp], i),
     }
     for name, (argtypes, restype) in sigs.items():

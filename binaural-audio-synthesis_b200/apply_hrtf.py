@@ -19,7 +19,9 @@ CPU path: without a CUDA device every compute call raises.
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
+import threading
 
 import numpy as np
 
@@ -236,7 +238,7 @@ def interpolate_2d_batch(irs_and_delaydiffs, elev, azim, az_kind=_cabi.AZ_F64, r
     return filt
 
 
-def _plan_and_synth(torch, dev, elev_d, azim_d, az_kind, n, mode, want_trace=False):
+def _plan_and_synth(torch, dev, elev_d, azim_d, az_kind, n, mode, want_trace=False, status=None):
     """plan_build + ir_synth for n directions already on the device; returns (filters, status
     int32[2], trace bytes or None), all asynchronous.  mode IR_PLANAR: filters (n, 2, K);
     IR_ROWS: (n, pitch, 2) filter rows for bas_render."""
@@ -249,7 +251,8 @@ def _plan_and_synth(torch, dev, elev_d, azim_d, az_kind, n, mode, want_trace=Fal
             raise ValueError('az_kind must have one entry per direction')
         kinds_ptr, kind_all = kinds_d.data_ptr(), 0
     terms = torch.empty((max(n, 1), 2 * _cabi.MAX_TERMS * 8), dtype=torch.uint8, device=dev.device)
-    status = torch.empty(2, dtype=torch.int32, device=dev.device)
+    if status is None:
+        status = torch.empty(2, dtype=torch.int32, device=dev.device)
     trace = torch.empty((max(n, 1), np.dtype(_cabi.TRACE_DTYPE).itemsize), dtype=torch.uint8,
                         device=dev.device) if want_trace else None
     _cabi.check(lib.bas_plan_build(dev.diffs[0].data_ptr(), dev.diffs[1].data_ptr(), dev.upsampling, dev.length,
@@ -327,6 +330,222 @@ def evaluate_trajectory(elev_azim_function, times):
     return elev, azim, kinds
 
 
+# Host arrays in, host arrays out: the render is cut into time segments of about this many output
+# bytes and upload / render / download of consecutive segments overlap on three streams.
+PIPELINE_SEGMENT_BYTES = 8 << 20
+PIPELINE_MAX_SEGMENTS = 64
+_SEGMENT_ALIGN = 8192            # output samples; a whole number of render tiles for every tile width
+
+_side_streams = {}
+TIMELINE = None                  # tools/e2e_timeline.py sets this to a list to collect (label, host time, event)
+
+
+def _mark(torch, label, stream=None):
+    if TIMELINE is not None:
+        import time
+        ev = None
+        if stream is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream)
+        TIMELINE.append((label, time.perf_counter(), ev))
+
+
+def _streams(torch, device):
+    """(upload, download) side streams of `device`, created once."""
+    st = _side_streams.get(device.index)
+    if st is None:
+        st = (torch.cuda.Stream(device=device), torch.cuda.Stream(device=device))
+        _side_streams[device.index] = st
+    return st
+
+
+def _segments(p0: int, p1: int, bytes_per_sample: int):
+    """Cut output samples [p0, p1) into pipeline segments at multiples of _SEGMENT_ALIGN."""
+    count = p1 - p0
+    if count <= 0:
+        return []
+    n_seg = max(1, min(PIPELINE_MAX_SEGMENTS, int(round(count * bytes_per_sample / PIPELINE_SEGMENT_BYTES))))
+    step = _round_up(-(-count // n_seg), _SEGMENT_ALIGN)
+    cuts = [p0]
+    while cuts[-1] < p1:
+        nxt = (cuts[-1] // _SEGMENT_ALIGN) * _SEGMENT_ALIGN + step
+        cuts.append(min(p1, nxt))
+    return list(zip(cuts[:-1], cuts[1:]))
+
+
+def _host_directions(elev_azim_functions) -> bool:
+    """True unless the caller passed pre-evaluated directions that already live on the device."""
+    if isinstance(elev_azim_functions, tuple) and len(elev_azim_functions) == 3 and not callable(elev_azim_functions[0]):
+        return not any(hasattr(v, 'is_cuda') and v.is_cuda for v in elev_azim_functions[:2])
+    return True
+
+
+def _directions(elev_azim_functions, n_src: int, n_in: int, chunksize: int):
+    """(elev, azim, kinds) at t = 0, C, ..., N_in for every source: arrays of n_src x (N_in/C + 1)
+    entries (numpy, or CUDA tensors when the caller passed those) and one az kind or an array."""
+    n_pts = n_in // chunksize + 1
+    if isinstance(elev_azim_functions, tuple) and len(elev_azim_functions) == 3 and not callable(elev_azim_functions[0]):
+        return elev_azim_functions
+    if len(elev_azim_functions) != n_src:
+        raise ValueError('need one trajectory per source')
+    times = np.arange(0, n_in + 1, chunksize, dtype=np.int64)
+    per = [evaluate_trajectory(f, times) for f in elev_azim_functions]
+    elev = per[0][0][None, :] if n_src == 1 else np.stack([p[0] for p in per])
+    azim = per[0][1][None, :] if n_src == 1 else np.stack([p[1] for p in per])
+    if all(np.isscalar(p[2]) for p in per) and len({p[2] for p in per}) == 1:
+        kinds = per[0][2]
+    else:
+        kinds = np.stack([np.broadcast_to(np.asarray(p[2], dtype=np.uint8), (n_pts,)) for p in per])
+    return elev, azim, kinds
+
+
+class _HostCache(threading.local):
+    """Per-thread, per-device scratch of the host pipeline, grown on demand and reused between calls
+    (every call ends with its device work complete, so nothing is in flight when they are reused)."""
+
+    def __init__(self):
+        self.arena, self.pinned = {}, {}
+
+    def device_arena(self, torch, device, nbytes):
+        a = self.arena.get(device.index)
+        if a is None or a.numel() < nbytes:
+            a = None
+            self.arena[device.index] = None
+            a = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
+            self.arena[device.index] = a
+        return a
+
+    def pinned_bytes(self, torch, name, nbytes):
+        b = self.pinned.get(name)
+        if b is None or b.numel() < nbytes:
+            b = torch.empty(max(int(nbytes * 1.25), 4096), dtype=torch.uint8, pin_memory=True)
+            self.pinned[name] = b
+        return b
+
+
+_host_cache = _HostCache()
+
+
+# Phases of the host pipeline: cumulative fractions of the output range.  The trajectory of phase
+# i+1 is evaluated on the host while phase i renders and travels back; a small first phase gets the
+# device -> host copy started early.  Jobs below PIPELINE_PHASE_MIN_BYTES run as one phase.
+PIPELINE_PHASES = (0.15, 0.5, 1.0)
+PIPELINE_PHASE_MIN_BYTES = 4 << 20
+
+
+def _phase_plan(p0: int, p1: int, n_in: int, chunksize: int, out_bytes_per_sample: int):
+    """[(p_from, p_to, pt_begin, pt_end)] per phase: output range and the chunk-boundary directions
+    that must be planned before it renders (every input below p_to needs both filters of its chunk)."""
+    n_pts = n_in // chunksize + 1
+    count = p1 - p0
+    fracs = PIPELINE_PHASES if count * out_bytes_per_sample >= PIPELINE_PHASE_MIN_BYTES else (1.0,)
+    cuts = [p0]
+    for f in fracs[:-1]:
+        c = min(p1, _round_up(p0 + int(f * count), _SEGMENT_ALIGN))
+        if c > cuts[-1]:
+            cuts.append(c)
+    if cuts[-1] < p1 or len(cuts) == 1:
+        cuts.append(p1)
+    phases, pt_done = [], 0
+    for i in range(len(cuts) - 1):
+        last = i == len(cuts) - 2
+        last_in = min(cuts[i + 1], n_in) - 1
+        pt_end = n_pts if last else min(n_pts, max(pt_done, last_in // chunksize + 2))
+        phases.append((cuts[i], cuts[i + 1], pt_done, pt_end))
+        pt_done = pt_end
+    return phases
+
+
+def _render_pipeline(torch, dev, src, chunksize, subchunksize, elev_azim_functions, mix, normalise, variant,
+                     p0, p1, return_peaks):
+    """render_sources for host signals and a host result: lib.bas_pipeline_upload / _phase."""
+    device = dev.device
+    n_src, n = src.shape
+    k = dev.taps
+    n_in = _round_up(n, chunksize)
+    n_pts = n_in // chunksize + 1
+    n_dirs = n_src * n_pts
+    count = p1 - p0
+    n_rows = 1 if mix else n_src
+    main = torch.cuda.current_stream()
+    up, down = _streams(torch, device)
+    offsets = (C.c_longlong * 8)()
+    need = lib.bas_pipeline_arena_bytes(n_src, n_in, chunksize, k, 1 if mix else 0, count, 0, offsets)
+    if need < 0:
+        raise BasError('bas_pipeline_arena_bytes: bad geometry')
+    arena = _host_cache.device_arena(torch, device, need)
+    workspace = _cabi.render_workspace(torch, device)
+    staged = _host_cache.pinned_bytes(torch, 'dirs', n_dirs * 17)
+    small = _host_cache.pinned_bytes(torch, 'small', 4 * (2 + n_src))
+    host_out = torch.empty((n_rows, 2, count), dtype=torch.float32, pin_memory=True)
+    job = _cabi.PipelineJob(
+        n_src=n_src, C=chunksize, S=subchunksize, K=k, U=dev.upsampling, mix=1 if mix else 0, variant=variant,
+        az_kind_all=_cabi.AZ_F64, n=n, n_in=n_in, p_begin=p0, p_count=count, x_host_stride=n,
+        segment_bytes=PIPELINE_SEGMENT_BYTES, x_host=src.data_ptr(), x_dev=None, dirs_host=staged.data_ptr(),
+        az_kind_host=staged.data_ptr() + n_dirs * 16, diffs_left_dev=dev.diffs[0].data_ptr(),
+        diffs_right_dev=dev.diffs[1].data_ptr(), bank_pp_dev=dev.bank_pp.data_ptr(), out_host=host_out.data_ptr(),
+        small_host=small.data_ptr(), arena_dev=arena.data_ptr(), arena_bytes=arena.numel(),
+        workspace_dev=workspace.data_ptr(), workspace_bytes=workspace.numel(),
+        stream_main=main.cuda_stream, stream_up=up.cuda_stream, stream_down=down.cuda_stream)
+    phases = _phase_plan(p0, p1, n_in, chunksize, 8 * n_rows)
+    cuts = (C.c_longlong * (len(phases) + 1))(*([ph[0] for ph in phases] + [p1]))
+    _cabi.check(lib.bas_pipeline_upload(C.byref(job), len(phases), cuts), 'bas_pipeline_upload')
+    staged_np = staged.numpy()
+    elev_h = staged_np[:n_dirs * 8].view(np.float64).reshape(n_src, n_pts)
+    azim_h = staged_np[n_dirs * 8:n_dirs * 16].view(np.float64).reshape(n_src, n_pts)
+    kinds_h = staged_np[n_dirs * 16:n_dirs * 17].reshape(n_src, n_pts)
+    pre = None
+    if isinstance(elev_azim_functions, tuple) and len(elev_azim_functions) == 3 and not callable(elev_azim_functions[0]):
+        pre = elev_azim_functions
+        if np.size(pre[0]) != n_dirs or np.size(pre[1]) != n_dirs:
+            raise ValueError('trajectories must give %d directions per source' % n_pts)
+        elev_h[:] = np.asarray(pre[0], dtype=np.float64).reshape(n_src, n_pts)
+        azim_h[:] = np.asarray(pre[1], dtype=np.float64).reshape(n_src, n_pts)
+        kinds_h[:] = np.broadcast_to(np.asarray(pre[2], dtype=np.uint8), (n_src, n_pts)) if not np.isscalar(pre[2]) else int(pre[2])
+    elif len(elev_azim_functions) != n_src:
+        raise ValueError('need one trajectory per source')
+    kinds_ptr = staged.data_ptr() + n_dirs * 16
+    for i, (pa, pb, pt0, pt1) in enumerate(phases):
+        # the trajectory of this phase is evaluated while the signal and the earlier phases travel
+        if pre is None and pt1 > pt0:
+            times = np.arange(pt0 * chunksize, (pt1 - 1) * chunksize + 1, chunksize, dtype=np.int64)
+            for s, fn in enumerate(elev_azim_functions):
+                e, a, kd = evaluate_trajectory(fn, times)
+                elev_h[s, pt0:pt1] = e
+                azim_h[s, pt0:pt1] = a
+                kinds_h[s, pt0:pt1] = kd
+        # one az kind for the whole phase (the usual case): the directions ride in the plan launches
+        first_kind = int(kinds_h[0, pt0]) if pt1 > pt0 else _cabi.AZ_F64
+        uniform = pt1 == pt0 or bool((kinds_h[:, pt0:pt1] == first_kind).all())
+        job.az_kind_all = first_kind
+        job.az_kind_host = None if uniform else kinds_ptr
+        _cabi.check(lib.bas_pipeline_phase(C.byref(job), i, len(phases), pt0, pt1, pa, pb), 'bas_pipeline_phase')
+    words = small.numpy()[:4 * (2 + n_src)].view(np.int32)
+    err, where = int(words[0]), int(words[1])
+    if err:
+        _raise_plan_error(err, ' (trajectory point %d of source %d)' % (where % n_pts, where // n_pts))
+    peaks_host = words[2:].view(np.float32).copy()
+    if normalise and count > 0 and (peaks_host > 1).any():
+        # apply_hrtf.py:462-464, the rare second pass: divide on the device, copy again
+        stride = int(offsets[7])
+        base = arena.data_ptr()
+        out_dev, peaks_dev, stream = base + offsets[6], base + offsets[4] + 8, main.cuda_stream
+        if mix:
+            gains = torch.from_numpy((1.0 / np.maximum(peaks_host, 1.0)).astype(np.float32)).to(device)
+            _cabi.check(lib.bas_render(base + offsets[5], n_in, n_in, n_src, n_in, chunksize, subchunksize, k, base + offsets[3],
+                                       gains.data_ptr(), p0, count, out_dev, stride, 1, None, variant, workspace.data_ptr(),
+                                       workspace.numel(), stream), 'bas_render')
+        else:
+            for s in np.nonzero(peaks_host > 1)[0]:
+                _cabi.check(lib.bas_normalise(out_dev + int(s) * 8 * stride, 2 * stride, peaks_dev + 4 * int(s), stream), 'bas_normalise')
+        _cabi.check(lib.bas_copy_2d(host_out.data_ptr(), 4 * count, out_dev, 4 * stride, 4 * count, 2 * n_rows, 0, stream), 'bas_copy_2d')
+        main.synchronize()
+    result = host_out.numpy()
+    if mix:
+        result = result[0]
+    return (result, peaks_host) if return_peaks else result
+
+
 def render_sources(signals, chunksize: int, subchunksize: int, elev_azim_functions, irs_and_delaydiffs,
                    mix=False, normalise=True, variant=_cabi.RENDER_AUTO, return_device=False,
                    time_range=None, return_peaks=False):
@@ -340,11 +559,17 @@ def render_sources(signals, chunksize: int, subchunksize: int, elev_azim_functio
     mix=True: returns (2, N_out): the sum over sources of what make_signal_move_2d returns for each
         (sources whose own peak exceeds 1 enter the sum divided by that peak when `normalise`).
     time_range=(p0, p1): only output samples p0 <= p < p1 are rendered and returned.
-    return_device: return CUDA tensors instead of numpy arrays (no host copy)."""
+    return_device: return CUDA tensors instead of numpy arrays (no host copy).
+
+    Host signals with a host result run as a pipeline over time segments: segment i+1 is uploaded
+    and segment i-1 downloaded while segment i renders (PCIe is full duplex), so the call costs
+    about one transfer of the larger direction instead of upload + render + download."""
     torch = _cabi.require_device()
     dev = _device_bank(irs_and_delaydiffs)
     device = dev.device
-    # ---- signals -> HBM, zero padded to a multiple of chunksize (apply_hrtf.py:405-406) ----------
+    main = torch.cuda.current_stream()
+    stream = main.cuda_stream
+    _mark(torch, 'start', main)
     if isinstance(signals, torch.Tensor):
         src = signals
     else:
@@ -354,82 +579,134 @@ def render_sources(signals, chunksize: int, subchunksize: int, elev_azim_functio
     n_src, n = src.shape
     k, n_in, n_out = render_geometry(n, chunksize, subchunksize, irs_and_delaydiffs)
     assert k == dev.taps
-    if src.is_cuda and src.dtype == torch.float32 and src.is_contiguous() and n == n_in and src.device == device:
+    p0, p1 = (0, n_out) if time_range is None else (int(time_range[0]), int(time_range[1]))
+    if not 0 <= p0 <= p1 <= n_out:
+        raise ValueError('time_range outside [0, %d]' % n_out)
+    count = p1 - p0
+    n_pts = n_in // chunksize + 1
+    if not src.is_cuda and not return_device and src.dtype == torch.float32 and _host_directions(elev_azim_functions):
+        return _render_pipeline(torch, dev, src, chunksize, subchunksize, elev_azim_functions, mix, normalise, variant,
+                                p0, p1, return_peaks)
+    up, down = _streams(torch, device)
+
+    # ---- signals: HBM-resident as they are, or uploaded (zero padded to a multiple of chunksize,
+    #      apply_hrtf.py:405-406).  The upload is issued first, on its own stream: it overlaps the
+    #      trajectory evaluation on the host and the plan / ir_synth kernels. --------------------------
+    resident = src.is_cuda and src.dtype == torch.float32 and src.is_contiguous() and n == n_in and src.device == device
+    uploaded = None
+    if resident:
         x = src
     else:
         x = torch.empty((n_src, n_in), dtype=torch.float32, device=device)
         if n_in > n:
             x[:, n:].zero_()
-        # pinned host memory is copied by DMA without a staging pass; pageable memory goes through
-        # the driver's bounce buffers
-        x[:, :n].copy_(src, non_blocking=(not src.is_cuda) and src.is_pinned())
-    n_pts = n_in // chunksize + 1
-    times = np.arange(0, n_in + 1, chunksize, dtype=np.int64)
-    if isinstance(elev_azim_functions, tuple) and len(elev_azim_functions) == 3 and not callable(elev_azim_functions[0]):
-        elev, azim, kinds = elev_azim_functions
+        if src.is_cuda:
+            x[:, :n].copy_(src)
+        elif count > 0:
+            lo = max(0, p0 - (k - 1)) // 4 * 4              # first and last input sample any output needs
+            hi = min(n, p1)
+            up.wait_stream(main)                            # x was just allocated on `main`
+            _cabi.check(lib.bas_copy_2d(x.data_ptr() + 4 * lo, 4 * n_in, src.data_ptr() + 4 * lo, 4 * n, 4 * (hi - lo), n_src, 1,
+                                        up.cuda_stream), 'bas_copy_2d')
+            uploaded = torch.cuda.Event()
+            uploaded.record(up)
+            _mark(torch, 'upload', up)
+
+    # ---- directions at the chunk boundaries -> HBM (one pinned staging buffer, one copy) ----------
+    elev, azim, kinds = _directions(elev_azim_functions, n_src, n_in, chunksize)
+    _mark(torch, 'h:trajectory')
+    if isinstance(elev, torch.Tensor) or isinstance(azim, torch.Tensor):
+        elev_d = torch.as_tensor(elev, dtype=torch.float64).to(device).contiguous()
+        azim_d = torch.as_tensor(azim, dtype=torch.float64).to(device).contiguous()
     else:
-        if len(elev_azim_functions) != n_src:
-            raise ValueError('need one trajectory per source')
-        per = [evaluate_trajectory(f, times) for f in elev_azim_functions]
-        elev = np.stack([p[0] for p in per])
-        azim = np.stack([p[1] for p in per])
-        if all(np.isscalar(p[2]) for p in per) and len({p[2] for p in per}) == 1:
-            kinds = per[0][2]
-        else:
-            kinds = np.stack([np.broadcast_to(np.asarray(p[2], dtype=np.uint8), (n_pts,)) for p in per])
-    elev_d = torch.as_tensor(elev, dtype=torch.float64).to(device).contiguous()
-    azim_d = torch.as_tensor(azim, dtype=torch.float64).to(device).contiguous()
+        if np.size(elev) != n_src * n_pts or np.size(azim) != n_src * n_pts:
+            raise ValueError('trajectories must give %d directions per source' % n_pts)
+        staged = torch.empty((2, n_src * n_pts), dtype=torch.float64, pin_memory=True)
+        host = staged.numpy()
+        host[0] = np.asarray(elev, dtype=np.float64).reshape(-1)
+        host[1] = np.asarray(azim, dtype=np.float64).reshape(-1)
+        both = staged.to(device, non_blocking=True)
+        elev_d, azim_d = both[0], both[1]
+        _mark(torch, 'h:staged')
     if elev_d.numel() != n_src * n_pts or azim_d.numel() != n_src * n_pts:
         raise ValueError('trajectories must give %d directions per source' % n_pts)
+    # status (2 ints) and per-source peaks share one buffer: one memset, one copy back
+    small_dev = torch.zeros(2 + n_src, dtype=torch.int32, device=device)
+    status, peaks = small_dev[:2], small_dev[2:].view(torch.float32)
+    _mark(torch, 'h:zeros')
+    filt, _, _ = _plan_and_synth(torch, dev, elev_d, azim_d, kinds, n_src * n_pts, _cabi.IR_ROWS, status=status)
+    _mark(torch, 'filters', main)
+    if uploaded is not None:
+        main.wait_event(uploaded)
 
-    filt, status, _ = _plan_and_synth(torch, dev, elev_d, azim_d, kinds, n_src * n_pts, _cabi.IR_ROWS)
-    p0, p1 = (0, n_out) if time_range is None else (int(time_range[0]), int(time_range[1]))
-    if not 0 <= p0 <= p1 <= n_out:
-        raise ValueError('time_range outside [0, %d]' % n_out)
-    count = p1 - p0
     stride = _round_up(max(count, 1), 4)
-    out = torch.empty((1 if mix else n_src, 2, stride), dtype=torch.float32, device=device)
-    peaks = torch.zeros(n_src, dtype=torch.float32, device=device)
-    stream = _stream(torch)
+    n_rows = 1 if mix else n_src
+    out = torch.empty((n_rows, 2, stride), dtype=torch.float32, device=device)
     workspace = _cabi.render_workspace(torch, device)
 
-    def launch(gains):
+    def launch(gains, pa, pb):
         _cabi.check(lib.bas_render(x.data_ptr(), n_in, n_in, n_src, n_in, chunksize, subchunksize, k,
                                    filt.data_ptr(), gains.data_ptr() if gains is not None else None,
-                                   p0, count, out.data_ptr(), stride, 1 if mix else 0, peaks.data_ptr(), variant,
-                                   workspace.data_ptr(), workspace.numel(), stream), 'bas_render')
+                                   pa, pb - pa, out.data_ptr() + 4 * (pa - p0), stride, 1 if mix else 0, peaks.data_ptr(),
+                                   variant, workspace.data_ptr(), workspace.numel(), stream), 'bas_render')
 
-    launch(None)
-    if normalise and not mix:
-        for s in range(n_src):        # apply_hrtf.py:462-464 per source, peak read on the device
-            _cabi.check(lib.bas_normalise(out[s].data_ptr(), 2 * stride, peaks[s:s + 1].data_ptr(), stream), 'bas_normalise')
-    # ---- results back: status + peaks and (unless return_device) the audio, one synchronisation ----
     small = torch.empty(2 + n_src, dtype=torch.int32, pin_memory=True)
-    small.copy_(torch.cat([status, peaks.view(torch.int32)]), non_blocking=True)
-    result = out[..., :count]
-    if mix:
-        result = result[0]
-    host_out = None
-    if not return_device:
-        # pinned destination from torch's caching host allocator: DMA straight into the array the
-        # caller receives (no pageable bounce, no extra host copy)
-        host_out = torch.empty(result.shape, dtype=torch.float32, pin_memory=True)
-        host_out.copy_(result, non_blocking=True)
-    torch.cuda.current_stream().synchronize()
+    host_out = None if return_device else torch.empty((n_rows, 2, count), dtype=torch.float32, pin_memory=True)
+
+    def download(pa, pb, st):
+        """out[:, :, pa-p0 : pb-p0] -> host_out, 2 * n_rows rows of (pb - pa) floats."""
+        _cabi.check(lib.bas_copy_2d(host_out.data_ptr() + 4 * (pa - p0), 4 * count, out.data_ptr() + 4 * (pa - p0), 4 * stride,
+                                    4 * (pb - pa), 2 * n_rows, 0, st.cuda_stream), 'bas_copy_2d')
+
+    def fetch_small(st):
+        _cabi.check(lib.bas_copy_2d(small.data_ptr(), 0, small_dev.data_ptr(), 0, 4 * (2 + n_src), 1, 0, st.cuda_stream), 'bas_copy_2d')
+
+    if host_out is not None and count > 0:
+        # ---- pipeline: segment i is downloaded while segment i+1 renders ------------------------------
+        down.wait_stream(main)                              # out was just allocated on `main`
+        for i, (pa, pb) in enumerate(_segments(p0, p1, 8 * n_rows)):
+            launch(None, pa, pb)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            down.wait_event(ev)
+            _mark(torch, 'render %d' % i, main)
+            download(pa, pb, down)
+            _mark(torch, 'down %d' % i, down)
+        fetch_small(down)
+        down.synchronize()
+        second_pass = normalise
+    else:
+        if count > 0:
+            launch(None, p0, p1)
+            if normalise and not mix:     # apply_hrtf.py:462-464 per source, peak read on the device
+                for s in range(n_src):
+                    _cabi.check(lib.bas_normalise(out[s].data_ptr(), 2 * stride, peaks[s:s + 1].data_ptr(), stream), 'bas_normalise')
+        second_pass = normalise and mix
+        fetch_small(main)
+        main.synchronize()
+
     host = small.numpy()
     err, where = int(host[0]), int(host[1])
     if err:
         _raise_plan_error(err, ' (trajectory point %d of source %d)' % (where % n_pts, where // n_pts))
     peaks_host = host[2:].view(np.float32).copy()
-    if normalise and mix and (peaks_host > 1).any():
-        gains = torch.from_numpy((1.0 / np.maximum(peaks_host, 1.0)).astype(np.float32)).to(device)
-        peaks.zero_()
-        launch(gains)
+    # ---- apply_hrtf.py:462-464: divide by the peak where it exceeds 1.  A second pass, needed only
+    #      when a peak does exceed 1 and the audio has already left (pipeline) or been mixed --------
+    if second_pass and count > 0 and (peaks_host > 1).any():
+        if mix:
+            gains = torch.from_numpy((1.0 / np.maximum(peaks_host, 1.0)).astype(np.float32)).to(device)
+            peaks.zero_()
+            launch(gains, p0, p1)
+        else:
+            for s in np.nonzero(peaks_host > 1)[0]:
+                _cabi.check(lib.bas_normalise(out[int(s)].data_ptr(), 2 * stride, peaks[int(s):int(s) + 1].data_ptr(), stream),
+                            'bas_normalise')
         if host_out is not None:
-            host_out.copy_(result, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-    if host_out is not None:
-        result = host_out.numpy()
+            download(p0, p1, main)
+        main.synchronize()
+    result = host_out.numpy() if host_out is not None else out[..., :count]
+    if mix:
+        result = result[0]
     return (result, peaks_host) if return_peaks else result
 
 

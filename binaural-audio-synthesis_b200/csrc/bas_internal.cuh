@@ -35,4 +35,13 @@ void bas_set_error(const char* fmt, ...);
         }                                                                               \
     } while (0)
 
+int bas_plan_build_range(const double* diffs_left_dev, const double* diffs_right_dev, int U, int L,
+                         const double* elev_dev, const double* azim_dev, const uint8_t* az_kind_dev,
+                         int az_kind_all, long long n_points, bas_term* terms_dev, bas_trace* trace_dev,
+                         int* status_dev, long long point_offset, int reset_status, void* stream);
+
+int bas_plan_build_inline(const double* diffs_left_dev, const double* diffs_right_dev, int U, int L,
+                          const double* elev_host, const double* azim_host, int az_kind_all, long long n_points,
+                          bas_term* terms_dev, int* status_dev, long long point_offset, void* stream);
+
 static inline long long bas_ceil_div(long long a, long long b) { return (a + b - 1) / b; }

@@ -45,17 +45,11 @@ extern "C" int bas_device_count(void) {
 // One thread per (trajectory point, ear): the ear-independent ring lookups are recomputed by both
 // threads of a point (cheap) so that all 2*n_points threads run independently; 64-thread CTAs spread
 // a 5169-point trajectory over every SM.
-__global__ void __launch_bounds__(64)
-bas_plan_kernel(const double* __restrict__ diffs_l, const double* __restrict__ diffs_r, int U, long long L,
-                const double* __restrict__ elev, const double* __restrict__ azim,
-                const uint8_t* __restrict__ az_kind, int az_kind_all, long long n_points,
-                BasTerm* __restrict__ terms, BasTrace* __restrict__ trace, int* __restrict__ status) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long p = t >> 1;
-    const int ear = (int)(t & 1);
-    if (p >= n_points) return;
-    const int kind = az_kind ? (int)az_kind[p] : az_kind_all;
-    const BasPointGeom g = bas_point_geom(elev[p], azim[p], kind);
+__device__ __forceinline__ void
+plan_thread(const double* __restrict__ diffs_l, const double* __restrict__ diffs_r, int U, long long L,
+            double elev, double azim, int kind, long long p, int ear,
+            BasTerm* __restrict__ terms, BasTrace* __restrict__ trace, int* __restrict__ status, long long point_offset) {
+    const BasPointGeom g = bas_point_geom(elev, azim, kind);
     BasTerm local[BAS_MAX_TERMS];
     long long lo[6], hi[6];
     const int err = g.err | bas_plan_point_ear(ear ? diffs_r : diffs_l, U, L, g, local, lo, hi);
@@ -79,21 +73,54 @@ bas_plan_kernel(const double* __restrict__ diffs_l, const double* __restrict__ d
     }
     if (err && status) {
         atomicOr(status, err);
-        atomicMin(status + 1, (int)(p > INT_MAX ? INT_MAX : p));
+        const long long idx = p + point_offset;              // index reported to the caller
+        atomicMin(status + 1, (int)(idx > INT_MAX ? INT_MAX : idx));
     }
 }
 
-extern "C" int bas_plan_build(const double* diffs_left_dev, const double* diffs_right_dev, int U, int L,
-                              const double* elev_dev, const double* azim_dev, const uint8_t* az_kind_dev,
-                              int az_kind_all, long long n_points, bas_term* terms_dev, bas_trace* trace_dev,
-                              int* status_dev, void* stream) {
+__global__ void __launch_bounds__(64)
+bas_plan_kernel(const double* __restrict__ diffs_l, const double* __restrict__ diffs_r, int U, long long L,
+                const double* __restrict__ elev, const double* __restrict__ azim,
+                const uint8_t* __restrict__ az_kind, int az_kind_all, long long n_points,
+                BasTerm* __restrict__ terms, BasTrace* __restrict__ trace, int* __restrict__ status,
+                long long point_offset) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long p = t >> 1;
+    if (p >= n_points) return;
+    plan_thread(diffs_l, diffs_r, U, L, elev[p], azim[p], az_kind ? (int)az_kind[p] : az_kind_all, p, (int)(t & 1),
+                terms, trace, status, point_offset);
+}
+
+// Directions carried in the kernel's own parameters (up to 32,764 bytes since CUDA 12.1): they reach
+// the device with the launch, through the command stream, instead of through a host -> device copy.
+// The host pipeline uses this while the copy engine is busy uploading the signal - a copy of the
+// directions would queue behind megabytes of samples (pipeline.cu).
+constexpr int kInlinePoints = 1984;                            // 2 x 1984 x 8 B = 31,744 B
+struct InlineDirs { double elev[kInlinePoints]; double azim[kInlinePoints]; };
+
+__global__ void __launch_bounds__(64)
+bas_plan_inline_kernel(const __grid_constant__ InlineDirs dirs, const double* __restrict__ diffs_l,
+                       const double* __restrict__ diffs_r, int U, long long L, int az_kind_all, int n_points,
+                       BasTerm* __restrict__ terms, int* __restrict__ status, long long point_offset) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = t >> 1;
+    if (p >= n_points) return;
+    plan_thread(diffs_l, diffs_r, U, L, dirs.elev[p], dirs.azim[p], az_kind_all, p, t & 1, terms, nullptr, status, point_offset);
+}
+
+// A range of a longer direction list: failing indices are reported as point_offset + i and the status
+// words are only reset on request (the host pipeline plans a trajectory in several phases).
+int bas_plan_build_range(const double* diffs_left_dev, const double* diffs_right_dev, int U, int L,
+                         const double* elev_dev, const double* azim_dev, const uint8_t* az_kind_dev,
+                         int az_kind_all, long long n_points, bas_term* terms_dev, bas_trace* trace_dev,
+                         int* status_dev, long long point_offset, int reset_status, void* stream) {
     BAS_CHECK_ARG(diffs_left_dev && diffs_right_dev && elev_dev && azim_dev && terms_dev, "null pointer");
     BAS_CHECK_ARG(U >= 1 && L >= U && L % U == 0 && L < (1 << 20), "need 1 <= U, U | L, L < 2^20");
     BAS_CHECK_ARG(az_kind_all >= 0 && az_kind_all <= 2, "az_kind_all");
     BAS_CHECK_ARG(n_points >= 0, "n_points");
     if (n_points == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (status_dev) {
+    if (status_dev && reset_status) {
         // {0, 0x7f7f7f7f}: memsets keep the call capturable in a CUDA graph
         BAS_CUDA(cudaMemsetAsync(status_dev, 0, sizeof(int), st));
         BAS_CUDA(cudaMemsetAsync(status_dev + 1, 0x7f, sizeof(int), st));
@@ -103,9 +130,38 @@ extern "C" int bas_plan_build(const double* diffs_left_dev, const double* diffs_
     BAS_CHECK_ARG(blocks < 0x7fffffffLL, "too many points for one launch");
     bas_plan_kernel<<<(unsigned)blocks, threads, 0, st>>>(
         diffs_left_dev, diffs_right_dev, U, (long long)L, elev_dev, azim_dev, az_kind_dev, az_kind_all, n_points,
-        reinterpret_cast<BasTerm*>(terms_dev), reinterpret_cast<BasTrace*>(trace_dev), status_dev);
+        reinterpret_cast<BasTerm*>(terms_dev), reinterpret_cast<BasTrace*>(trace_dev), status_dev, point_offset);
     BAS_LAUNCH_CHECK();
     return 0;
+}
+
+// HOST direction arrays, one az kind for all: planned in launches of kInlinePoints directions each.
+int bas_plan_build_inline(const double* diffs_left_dev, const double* diffs_right_dev, int U, int L,
+                          const double* elev_host, const double* azim_host, int az_kind_all, long long n_points,
+                          bas_term* terms_dev, int* status_dev, long long point_offset, void* stream) {
+    BAS_CHECK_ARG(diffs_left_dev && diffs_right_dev && elev_host && azim_host && terms_dev, "null pointer");
+    BAS_CHECK_ARG(U >= 1 && L >= U && L % U == 0 && L < (1 << 20), "need 1 <= U, U | L, L < 2^20");
+    BAS_CHECK_ARG(az_kind_all >= 0 && az_kind_all <= 2, "az_kind_all");
+    BAS_CHECK_ARG(n_points >= 0, "n_points");
+    static thread_local InlineDirs dirs;                        // copied into the launch by cudaLaunchKernel
+    for (long long first = 0; first < n_points; first += kInlinePoints) {
+        const int m = (int)(n_points - first < kInlinePoints ? n_points - first : kInlinePoints);
+        memcpy(dirs.elev, elev_host + first, (size_t)m * 8);
+        memcpy(dirs.azim, azim_host + first, (size_t)m * 8);
+        bas_plan_inline_kernel<<<(unsigned)bas_ceil_div(2 * m, 64), 64, 0, (cudaStream_t)stream>>>(
+            dirs, diffs_left_dev, diffs_right_dev, U, (long long)L, az_kind_all, m,
+            reinterpret_cast<BasTerm*>(terms_dev) + first * 2 * BAS_MAX_TERMS, status_dev, point_offset + first);
+        BAS_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+extern "C" int bas_plan_build(const double* diffs_left_dev, const double* diffs_right_dev, int U, int L,
+                              const double* elev_dev, const double* azim_dev, const uint8_t* az_kind_dev,
+                              int az_kind_all, long long n_points, bas_term* terms_dev, bas_trace* trace_dev,
+                              int* status_dev, void* stream) {
+    return bas_plan_build_range(diffs_left_dev, diffs_right_dev, U, L, elev_dev, azim_dev, az_kind_dev, az_kind_all,
+                                n_points, terms_dev, trace_dev, status_dev, 0, 1, stream);
 }
 
 // ---- host twins (same plan_math.h) -----------------------------------------------------------

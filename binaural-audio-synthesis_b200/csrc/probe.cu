@@ -94,11 +94,72 @@ bas_probe_fir_kernel(int iters, float* __restrict__ sink) {
     sink[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// mode 4: the same 32x32 block of packed FMAs visited diagonal by diagonal: one tap pair w is reused by
+// 32 consecutive FFMA2 while the x scalar and the accumulator change (x[32] lives in registers).
+// mode 5: as mode 4 with scalar fma.rn.f32.
+template <int MODE>
+__global__ void __launch_bounds__(128)
+bas_probe_diag_kernel(int iters, float* __restrict__ sink) {
+    const float seed = (float)(threadIdx.x & 7) * 1e-3f;
+    float s = 0.f;
+    float x[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) x[i] = 0.5f + seed + 1e-3f * i;
+    if (MODE == 4) {
+        unsigned long long acc[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) asm("mov.b64 %0, {%1, %2};" : "=l"(acc[i]) : "f"(seed + i), "f"(seed - i));
+        float wl = 1e-3f + seed, wr = 2e-3f;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                unsigned long long w;
+                asm volatile("mov.b64 %0, {%1, %2};" : "=l"(w) : "f"(wl), "f"(wr));
+#pragma unroll
+                for (int m = 0; m < 32; ++m) {
+                    unsigned long long xx;
+                    asm("mov.b64 %0, {%1, %1};" : "=l"(xx) : "f"(x[m]));
+                    asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[(m + j) & 31]) : "l"(xx), "l"(w));
+                }
+                wl = wl * 0.999f + 1e-4f; wr = wr * 0.998f + 1e-4f;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[i])); s += lo + hi; }
+    } else {
+        float accl[32], accr[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { accl[i] = seed + i; accr[i] = seed - i; }
+        float wl = 1e-3f + seed, wr = 2e-3f;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+#pragma unroll
+                for (int m = 0; m < 32; ++m) {
+                    asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(accl[(m + j) & 31]) : "f"(x[m]), "f"(wl));
+                    asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(accr[(m + j) & 31]) : "f"(x[m]), "f"(wr));
+                }
+                wl = wl * 0.999f + 1e-4f; wr = wr * 0.998f + 1e-4f;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) s += accl[i] + accr[i];
+    }
+    sink[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace
 
 extern "C" int bas_probe_fma(int packed, int blocks, int threads, int iters, float* sink_dev, void* stream) {
     BAS_CHECK_ARG(sink_dev, "null pointer");
     BAS_CHECK_ARG(blocks >= 1 && threads >= 32 && threads <= 256 && threads % 32 == 0 && iters >= 1, "launch shape");
+    if (packed == 4 || packed == 5) {
+        BAS_CHECK_ARG(threads <= 128, "FIR probes use at most 128 threads per block");
+        if (packed == 4) bas_probe_diag_kernel<4><<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, sink_dev);
+        else bas_probe_diag_kernel<5><<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, sink_dev);
+        BAS_LAUNCH_CHECK();
+        return 0;
+    }
     if (packed == 2 || packed == 3) {       // FIR-shaped streams: FMA count = blocks * threads * iters * 2048
         BAS_CHECK_ARG(threads <= 128, "FIR probes use at most 128 threads per block");
         if (packed == 2) bas_probe_fir_kernel<2><<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, sink_dev);

@@ -1,0 +1,21 @@
+// Host <-> HBM transfers of the render pipeline.  make_signal_move_2d takes a host signal and returns
+// a host array (apply_hrtf.py:356, :459-466); the host side cuts the signal into time segments and
+// overlaps upload, render and download of consecutive segments on three streams.  These are the
+// copies it issues: plain asynchronous DMA, one call each (no batched-copy API).
+#include "bas_internal.cuh"
+
+extern "C" int bas_copy_2d(void* dst, long long dst_pitch_bytes, const void* src, long long src_pitch_bytes,
+                           long long width_bytes, long long rows, int to_device, void* stream) {
+    BAS_CHECK_ARG(dst && src, "null pointer");
+    BAS_CHECK_ARG(width_bytes >= 0 && rows >= 0, "negative extent");
+    if (width_bytes == 0 || rows == 0) return 0;
+    const cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    if (rows == 1 || (dst_pitch_bytes == width_bytes && src_pitch_bytes == width_bytes)) {
+        BAS_CUDA(cudaMemcpyAsync(dst, src, (size_t)(width_bytes * rows), kind, (cudaStream_t)stream));
+        return 0;
+    }
+    BAS_CHECK_ARG(dst_pitch_bytes >= width_bytes && src_pitch_bytes >= width_bytes, "pitch smaller than a row");
+    BAS_CUDA(cudaMemcpy2DAsync(dst, (size_t)dst_pitch_bytes, src, (size_t)src_pitch_bytes, (size_t)width_bytes,
+                               (size_t)rows, kind, (cudaStream_t)stream));
+    return 0;
+}

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define BAS_ABI_VERSION 1
+#define BAS_ABI_VERSION 2
 
 #define BAS_N_DIRECTIONS 187      /* rows of the measurement grid, sphere.py:127-315 */
 #define BAS_MAX_TERMS 16          /* merged gather terms per ear per trajectory point */
@@ -151,6 +151,71 @@ int bas_normalise(float* out_dev, long long n, const float* peak_dev, void* stre
 
 /* max over n floats of |v| into *peak_dev (atomic max; zero it first). */
 int bas_peak(const float* v_dev, long long n, float* peak_dev, void* stream);
+
+/* ---- host <-> HBM copies of the segment pipeline (make_signal_move_2d takes and returns host
+ *      arrays, apply_hrtf.py:356, :459-466) ---------------------------------------------------
+ * Asynchronous copy of `rows` rows of width_bytes each on `stream`; to_device != 0: host -> device,
+ * else device -> host.  Pinned host memory is copied by DMA without staging. */
+int bas_copy_2d(void* dst, long long dst_pitch_bytes, const void* src, long long src_pitch_bytes,
+                long long width_bytes, long long rows, int to_device, void* stream);
+
+/* ---- make_signal_move_2d with host buffers (apply_hrtf.py:356-466): upload, plan, ir_synth,
+ *      segmented render and download as one pipeline over three streams ------------------------
+ * The output range is cut into 1..8 PHASES along time (p_cuts[0..n_phases]).
+ * bas_pipeline_upload enqueues the signal upload phase by phase (and the zero padding of
+ * apply_hrtf.py:405-406) on stream_up and returns at once.  For every phase, in order, the caller
+ * evaluates the trajectory at the phase's chunk boundaries into dirs_host (the reference's
+ * elev_azim_function is host code, apply_hrtf.py:429/:435) and calls bas_pipeline_phase: it enqueues
+ * the copy of directions [pt_begin, pt_end) of every source, their plan and filter rows, the render
+ * of output samples [p_from, p_to) in time segments on stream_main, and the copy of each finished
+ * segment to out_host on stream_down.  Only the last phase blocks: it returns when out_host and
+ * small_host are complete.  All calls of a job must come from one host thread.  The peak division of
+ * apply_hrtf.py:462-464 is NOT applied: the caller reads the peaks from small_host and, in the
+ * rare case that one exceeds 1, runs bas_normalise on the arena's output block and copies again. */
+typedef struct bas_pipeline_job {
+    int n_src;                    /* mono sources of equal length */
+    int C, S, K, U;               /* chunksize, subchunksize, taps, upsampling of the bank */
+    int mix;                      /* 0: n_src x 2 x p_count result, 1: one 2 x p_count mix */
+    int variant;                  /* bas_render variant */
+    int az_kind_all;              /* BAS_AZ_* of every direction when az_kind_host is NULL */
+    long long n;                  /* samples per source */
+    long long n_in;               /* n rounded up to a multiple of C */
+    long long p_begin, p_count;   /* rendered output range */
+    long long x_host_stride;      /* floats between sources in x_host */
+    long long segment_bytes;      /* target size of a downloaded segment (0: a single segment) */
+    const float* x_host;          /* n_src x n (pinned for DMA without staging), or NULL with x_dev */
+    const float* x_dev;           /* optional HBM-resident n_src x n_in signals (zero padded) */
+    const double* dirs_host;      /* elev[n_src * n_pts] then azim[n_src * n_pts], n_pts = n_in / C + 1 */
+    const uint8_t* az_kind_host;  /* n_src * n_pts bytes, or NULL: az_kind_all for every direction
+                                     (then the directions travel inside the plan launches) */
+    const double* diffs_left_dev; /* bank: delay tables and polyphase HRIRs (bas_bank_to_polyphase) */
+    const double* diffs_right_dev;
+    const float* bank_pp_dev;
+    float* out_host;              /* [n_rows][2][p_count], n_rows = mix ? 1 : n_src (pinned) */
+    int32_t* small_host;          /* 2 + n_src words (pinned): error bits, first failing direction,
+                                     then the per-source peaks as float bits */
+    void* arena_dev;              /* bas_pipeline_arena_bytes() bytes, 256-byte aligned */
+    long long arena_bytes;
+    void* workspace_dev;          /* bas_render workspace (may be NULL) */
+    long long workspace_bytes;
+    void* stream_main;            /* three distinct streams */
+    void* stream_up;
+    void* stream_down;
+} bas_pipeline_job;
+
+/* Bytes of device scratch a job needs.  offsets (may be NULL) receives the byte offsets of
+ * {directions, az kinds, plan terms, filter rows, status+peaks, signals, output} and, in
+ * offsets[7], the output row stride in floats (out[row][ear][stride]). */
+long long bas_pipeline_arena_bytes(int n_src, long long n_in, int C, int K, int mix, long long p_count,
+                                   int resident_x, long long* offsets);
+int bas_pipeline_upload(const bas_pipeline_job* job, int n_phases, const long long* p_cuts);
+int bas_pipeline_phase(const bas_pipeline_job* job, int phase, int n_phases, long long pt_begin, long long pt_end,
+                       long long p_from, long long p_to);
+
+/* Debug aid: returns (in buf) the timeline of the pipeline calls made on this thread since tracing was
+ * enabled - host time of every enqueue, device time of its completion - then clears it and switches
+ * tracing on or off. */
+int bas_pipeline_trace(int enable, char* buf, size_t len);
 
 /* FP32 pipe probe used by bench.py to state the measured FMA peak beside the HBM roofline:
  * every thread runs `iters` rounds of 16 independent dependent-chain FMAs.

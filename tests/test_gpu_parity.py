@@ -247,3 +247,44 @@ def test_load_irs_and_delaydiffs_roundtrip(bas, tmp_path, golden_bank):
     assert np.array_equal(bank.irs_left, golden_bank.irs_left[:, :128])
     got = bas.interpolate_2d(bank, 0.3, 2.0)
     assert got.shape == (2, 16)
+
+
+@pytest.mark.parametrize('phases,seg_bytes', [((1.0,), 0), ((0.3, 1.0), 1 << 20), ((0.1, 0.35, 0.6, 1.0), 256 << 10)])
+def test_host_pipeline_equals_device_path(bas, synth_bank, phases, seg_bytes, monkeypatch):
+    """Host arrays in / host array out run as a phased pipeline (bas_pipeline_upload / _phase: upload,
+    plan, ir_synth, segmented render and download on three streams).  Cutting the job along time must
+    not change a bit: every output sample is computed by the same instructions in the same order as
+    in the one-launch, device-resident path."""
+    import torch
+    ah = bas.apply_hrtf
+    monkeypatch.setattr(ah, 'PIPELINE_PHASES', phases)
+    monkeypatch.setattr(ah, 'PIPELINE_PHASE_MIN_BYTES', 0)
+    monkeypatch.setattr(ah, 'PIPELINE_SEGMENT_BYTES', seg_bytes)
+    rng = np.random.default_rng(77)
+    n_src, n = 3, 150_000 + 77
+    x = (0.02 * rng.standard_normal((n_src, n))).astype(np.float32)
+    x[1] *= 300.0                                            # peaks above 1: the second (normalising) pass
+    k = 2 * np.pi / 40_000
+    def vec(s):
+        def fn(t):
+            return (np.deg2rad(20 + 60 * np.sin((2 + s) * k * t + s)), ((3 + s) * k * t + 0.5 * s) % (2 * np.pi))
+        fn.vectorized = True
+        return fn
+    trajs = [vec(0), vec(1), lambda t: (np.float64(0.3 * np.cos(k * t)), np.float64((2 * k * t) % (2 * np.pi)))]
+    xd = torch.zeros((n_src, (n + 511) // 512 * 512), dtype=torch.float32, device='cuda')
+    xd[:, :n] = torch.from_numpy(x).cuda()
+    for mix in (False, True):
+        want, want_peaks = bas.render_sources(xd, 512, 32, trajs, synth_bank, mix=mix, return_device=True, return_peaks=True)
+        got, got_peaks = bas.render_sources(x, 512, 32, trajs, synth_bank, mix=mix, return_peaks=True)
+        assert isinstance(got, np.ndarray) and got.dtype == np.float32
+        assert np.array_equal(got, want.cpu().numpy())
+        assert np.array_equal(got_peaks, want_peaks) and got_peaks[1] > 1
+    # a window of the output, pinned input, and directions given as arrays instead of callables
+    times = np.arange(0, xd.shape[1] + 1, 512)
+    pre = (np.stack([np.broadcast_to(np.asarray(f(times)[0] if getattr(f, 'vectorized', False) else [f(int(t))[0] for t in times], dtype=np.float64), times.shape) for f in trajs]),
+           np.stack([np.asarray(f(times)[1] if getattr(f, 'vectorized', False) else [f(int(t))[1] for t in times], dtype=np.float64) for f in trajs]),
+           bas._cabi.AZ_F64)
+    xp = torch.from_numpy(x).pin_memory().numpy()
+    full = bas.render_sources(xd, 512, 32, pre, synth_bank, normalise=False, return_device=True).cpu().numpy()
+    part = bas.render_sources(xp, 512, 32, pre, synth_bank, normalise=False, time_range=(12_345, 140_001))
+    assert np.array_equal(part, full[:, :, 12_345:140_001])

@@ -33,6 +33,6 @@ def run(mode, blocks, threads, iters, fma_per_thread_iter):
 out = {}
 for name, mode, per in (('chain_f32', 0, 32), ('chain_f32x2', 1, 32)):
     out[name] = {w: round(run(mode, 148 * (w // 4), 128, 4096, per), 2) for w in (4, 8, 16, 32)}
-for name, mode in (('fir_f32x2', 2), ('fir_f32', 3)):
-    out[name] = {w: round(run(mode, 148 * (w // 4), 128, 64, 2048), 2) for w in (4, 8, 12, 16)}
+for name, mode in (('fir_f32x2', 2), ('fir_f32', 3), ('diag_f32x2', 4), ('diag_f32', 5)):
+    out[name] = {w: round(run(mode, 148 * (w // 4), 128, 64, 2048), 2) for w in (4, 8, 12, 16, 20)}
 print(json.dumps(out, indent=1))
