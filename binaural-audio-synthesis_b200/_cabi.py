@@ -20,6 +20,18 @@ E_ARG, E_UNSUPPORTED, E_NO_DEVICE = -1, -2, -3
 RENDER_AUTO, RENDER_GENERIC, RENDER_TILED = 0, 1, 2
 RENDER_SPLIT, RENDER_NO_SPLIT = 0x40, 0x80
 IR_UPSAMPLED, IR_PLANAR, IR_ROWS = 0, 1, 2
+TILED_SHAPES = ((4, 2, 2), (4, 1, 2), (4, 1, 3), (6, 1, 2), (6, 2, 1), (8, 2, 1), (8, 1, 1))   # (warps per CTA, stages, CTAs per SM)
+
+
+def render_variant(tw=0, ns=0, ctas=0, parts=0, split=None, base=RENDER_TILED):
+    """bas_render variant word that requests a tile shape of the tiled kernel (0 = chosen by the library):
+    tw warps per CTA, ns pipeline stages, ctas resident CTAs per SM, parts (1, 2, 4, 8) warps per
+    1024-output stripe; split True / False forces / forbids splitting tiles between CTAs."""
+    code = {0: 0, 1: 1, 2: 2, 4: 3, 8: 4}[parts]
+    v = base | (tw << 8) | (ns << 16) | (ctas << 24) | (code << 28)
+    if split is not None:
+        v |= RENDER_SPLIT if split else RENDER_NO_SPLIT
+    return v
 
 
 class Term(C.Structure):

@@ -68,65 +68,47 @@ bas_ir_synth_kernel(const float* __restrict__ bank_pp, int U, int K, const BasTe
 }
 
 // filter-row layout for the renderer: both ears per thread, out[point][m][ear] with taps K..pitch-1
-// zeroed (bas_filter_row_pitch).  A CTA walks over kPointsPerCta CONSECUTIVE trajectory points:
-// neighbouring points use the same bank rows and, delays moving by a fraction of a sample per chunk,
-// mostly the same phase rows, so their gathers hit in L1 instead of going back to L2.
-constexpr int kPointsPerCta = 1;
-
+// zeroed (bas_filter_row_pitch).  One CTA per trajectory point.  The kernel is bound by the latency of
+// its gathers (the bank sits in L2), so all 2 x 16 of a tap are issued as independent loads before the
+// first is consumed: terms stay in their fixed plan slots, a slot with weight zero reads column 0 of
+// the bank with weight zero (adds exactly nothing), and the sum runs over the slots in order.
 __global__ void __launch_bounds__(kThreads)
 bas_ir_synth_rows_kernel(const float* __restrict__ bank_pp, int U, int K, int pitch, long long n_points,
                          const BasTermDev* __restrict__ terms, float2* __restrict__ out) {
     const int L = U * K;
-    __shared__ int s_base[2][2][kMaxTerms];
-    __shared__ int s_adv[2][2][kMaxTerms];
-    __shared__ float s_w[2][2][kMaxTerms];
-    __shared__ int s_n[2][2];
-    const long long first = (long long)blockIdx.x * kPointsPerCta;
-    // warps 0 and 1 compact the non-zero terms of the two ears of point `pt` into buffer `buf`
-    auto load_terms = [&](long long pt, int buf) {
-        if (threadIdx.x < 64 && pt < n_points) {
-            const int ear = threadIdx.x >> 5, lane = threadIdx.x & 31;
-            BasTermDev t; t.row_shift = 0; t.weight = 0.f;
-            if (lane < kMaxTerms) t = terms[(pt * 2 + ear) * kMaxTerms + lane];
-            const bool live = t.weight != 0.f;
-            const unsigned mask = __ballot_sync(0xffffffffu, live);
-            if (live) {
-                const int slot = __popc(mask & ((1u << lane) - 1u));
-                const int row = t.row_shift >> 20, shift = t.row_shift & 0xFFFFF;
-                const int ph = (U - shift % U) % U;
-                s_base[buf][ear][slot] = (ear * BAS_N_DIRECTIONS + row) * L + ph * K;
-                s_adv[buf][ear][slot] = (shift + ph) / U;
-                s_w[buf][ear][slot] = t.weight;
-            }
-            if (lane == 0) s_n[buf][ear] = __popc(mask);
-        }
-    };
-    load_terms(first, 0);
+    __shared__ int s_base[2 * kMaxTerms];        // float offset of the phase row inside the bank (both ears)
+    __shared__ int s_adv[2 * kMaxTerms];         // column advance a = ceil(shift / U)
+    __shared__ float s_w[2 * kMaxTerms];
+    const long long point = blockIdx.x;
+    if (threadIdx.x < 2 * kMaxTerms) {
+        const int ear = threadIdx.x / kMaxTerms;
+        const BasTermDev t = terms[point * 2 * kMaxTerms + threadIdx.x];
+        const bool live = t.weight != 0.f;
+        const int row = t.row_shift >> 20, shift = t.row_shift & 0xFFFFF;
+        const int ph = (U - shift % U) % U;
+        s_base[threadIdx.x] = live ? (ear * BAS_N_DIRECTIONS + row) * L + ph * K : 0;
+        s_adv[threadIdx.x] = live ? (shift + ph) / U : 0;
+        s_w[threadIdx.x] = t.weight;
+    }
     __syncthreads();
-    for (int i = 0; i < kPointsPerCta; ++i) {
-        const long long point = first + i;
-        if (point >= n_points) break;
-        const int buf = i & 1;
-        load_terms(point + 1 < first + kPointsPerCta ? point + 1 : n_points, buf ^ 1);   // prefetch the next table
-        const int n_l = s_n[buf][0], n_r = s_n[buf][1];
-        float2* dst = out + point * pitch;
-        for (int m = threadIdx.x; m < pitch; m += kThreads) {
-            float acc_l = 0.f, acc_r = 0.f;
-            if (m < K) {
-                for (int t = 0; t < n_l; ++t) {
-                    int j = m - s_adv[buf][0][t];
-                    j += (j < 0) ? K : 0;
-                    acc_l = fmaf(s_w[buf][0][t], __ldg(bank_pp + s_base[buf][0][t] + j), acc_l);
-                }
-                for (int t = 0; t < n_r; ++t) {
-                    int j = m - s_adv[buf][1][t];
-                    j += (j < 0) ? K : 0;
-                    acc_r = fmaf(s_w[buf][1][t], __ldg(bank_pp + s_base[buf][1][t] + j), acc_r);
-                }
+    float2* dst = out + point * pitch;
+    for (int m = threadIdx.x; m < pitch; m += kThreads) {
+        float acc_l = 0.f, acc_r = 0.f;
+        if (m < K) {
+            float v[2 * kMaxTerms];
+#pragma unroll
+            for (int t = 0; t < 2 * kMaxTerms; ++t) {
+                int j = m - s_adv[t];
+                j += (j < 0) ? K : 0;
+                v[t] = __ldg(bank_pp + s_base[t] + j);
             }
-            dst[m] = make_float2(acc_l, acc_r);
+#pragma unroll
+            for (int t = 0; t < kMaxTerms; ++t) {
+                acc_l = fmaf(s_w[t], v[t], acc_l);
+                acc_r = fmaf(s_w[kMaxTerms + t], v[kMaxTerms + t], acc_r);
+            }
         }
-        __syncthreads();
+        dst[m] = make_float2(acc_l, acc_r);
     }
 }
 
@@ -172,7 +154,7 @@ extern "C" int bas_ir_synth(const float* bank_pp_dev, int U, int K, const bas_te
     const BasTermDev* terms = reinterpret_cast<const BasTermDev*>(terms_dev);
     if (mode == BAS_IR_ROWS) {
         BAS_CHECK_ARG((reinterpret_cast<uintptr_t>(out_dev) & 15) == 0, "filter rows must be 16-byte aligned");
-        bas_ir_synth_rows_kernel<<<(unsigned)bas_ceil_div(n_points, kPointsPerCta), kThreads, 0, st>>>(
+        bas_ir_synth_rows_kernel<<<(unsigned)n_points, kThreads, 0, st>>>(
             bank_pp_dev, U, K, bas_filter_row_pitch(K), n_points, terms, reinterpret_cast<float2*>(out_dev));
     } else if (mode == BAS_IR_PLANAR) {
         dim3 grid((unsigned)n_points, 2);

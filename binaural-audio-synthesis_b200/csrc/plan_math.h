@@ -167,6 +167,17 @@ BAS_HD int32_t bas_pack_term(int row, long long shift, long long L) {
     if (s < 0) s += L;
     return (int32_t)(((long long)row << 20) | s);
 }
+// A run of n consecutive shifts base, base + 1, ...: one modulo (64-bit division is a subroutine on the
+// device), then increments that wrap at L.
+#define BAS_PACK_RUN(out, first, n, row, base, L)                                        \
+    do {                                                                                 \
+        long long s_ = (base) % (L);                                                     \
+        if (s_ < 0) s_ += (L);                                                           \
+        _Pragma("unroll") for (int i_ = 0; i_ < (n); ++i_) {                             \
+            (out)[(first) + i_].row_shift = (int32_t)(((long long)(row) << 20) | s_);    \
+            if (++s_ == (L)) s_ = 0;                                                     \
+        }                                                                                \
+    } while (0)
 
 // out[0..n] = scale * in[0..n-1] * (p.c0 + p.c1 z)
 #define BAS_POLY_MUL(out, in, n, p)                                  \
@@ -278,22 +289,22 @@ BAS_HD int bas_plan_point_ear(const double* diffs, int upsampling, long long L, 
     BAS_POLY_MUL(ba5, ba4, 4, p1b);
     const long long base_tb = vs.lo + rt.res.lo, base_ta = base_tb + rt.rem.lo;
     const long long base_bb = vs.lo + vr.lo + rb.res.lo, base_ba = base_bb + rb.rem.lo;
+    BAS_PACK_RUN(out, 0, 3, g.top.before, base_tb, L);
+    BAS_PACK_RUN(out, 3, 4, g.top.after, base_ta, L);
+    BAS_PACK_RUN(out, 7, 4, g.bot.before, base_bb, L);
+    BAS_PACK_RUN(out, 11, 5, g.bot.after, base_ba, L);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int i = 0; i < 3; ++i) { out[i].row_shift = bas_pack_term(g.top.before, base_tb + i, L); out[i].weight = (float)tb3[i]; }
+    for (int i = 0; i < 3; ++i) out[i].weight = (float)tb3[i];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int i = 0; i < 4; ++i) { out[3 + i].row_shift = bas_pack_term(g.top.after, base_ta + i, L); out[3 + i].weight = (float)ta4[i]; }
+    for (int i = 0; i < 4; ++i) { out[3 + i].weight = (float)ta4[i]; out[7 + i].weight = (float)bb4[i]; }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int i = 0; i < 4; ++i) { out[7 + i].row_shift = bas_pack_term(g.bot.before, base_bb + i, L); out[7 + i].weight = (float)bb4[i]; }
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int i = 0; i < 5; ++i) { out[11 + i].row_shift = bas_pack_term(g.bot.after, base_ba + i, L); out[11 + i].weight = (float)ba5[i]; }
+    for (int i = 0; i < 5; ++i) out[11 + i].weight = (float)ba5[i];
     return err;
 }
 

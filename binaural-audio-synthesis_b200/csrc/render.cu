@@ -39,12 +39,6 @@
 
 using namespace bas_render_detail;
 
-namespace bas_render_detail {
-BAS_DECLARE_TILED(2)
-BAS_DECLARE_TILED(4)
-BAS_DECLARE_TILED(8)
-}
-
 namespace {
 
 // ------------------------------------------------------------------------------------------------
@@ -152,41 +146,58 @@ extern "C" int bas_render(const float* x_dev, long long x_stride, long long n_va
         return BAS_E_UNSUPPORTED;
     }
     if (base != BAS_RENDER_GENERIC && tiled_ok) {
-        // Tile shape: TW warps per CTA x NS pipeline stages.  Variant bits 8..15 request a TW, bits
-        // 16..23 an NS; otherwise take the shape that keeps most warps resident (shared memory is the
-        // limit: long filters leave room for fewer stages / warps), preferring two stages, then the
-        // measured-best width (4 for one source per tile, 8 when mixing).
-        const int tw_req = (variant >> 8) & 0xff, ns_req = (variant >> 16) & 0xff;
-        struct Shape { int tw, ns; };
-        const Shape pref_one[6] = {{4, 2}, {8, 2}, {2, 2}, {8, 1}, {4, 1}, {2, 1}};
-        const Shape pref_mix[6] = {{8, 2}, {4, 2}, {2, 2}, {8, 1}, {4, 1}, {2, 1}};
-        const Shape* pref = prm.mix ? pref_mix : pref_one;
-        auto warps = [&](Shape sh) -> int {
-#define BAS_W(TW_, NS_) if (sh.tw == TW_ && sh.ns == NS_) return prm.mix ? tiled_warps_per_sm<TW_, true, NS_>(K, C, prm.pitch) : tiled_warps_per_sm<TW_, false, NS_>(K, C, prm.pitch)
-            BAS_W(2, 1); BAS_W(2, 2); BAS_W(4, 1); BAS_W(4, 2); BAS_W(8, 1); BAS_W(8, 2);
-#undef BAS_W
-            return 0;
-        };
-        Shape best = {0, 0};
-        int best_warps = 0;
-        for (int i = 0; i < 6; ++i) {
-            if (tw_req && pref[i].tw != tw_req) continue;
-            if (ns_req && pref[i].ns != ns_req) continue;
-            const int w = warps(pref[i]);
-            if (w > best_warps) { best_warps = w; best = pref[i]; }
+        // Tile shape: TW warps per CTA x NS pipeline stages x CTAs per SM, and `parts` warps per
+        // 1024-output stripe.  Variant bits 8..15 request a TW, 16..23 an NS, 24..27 a CTA count per SM,
+        // 28..30 parts (code n: 2^(n-1)); otherwise the shape with the lowest estimated time is taken.
+        const int tw_req = (variant >> 8) & 0xff, ns_req = (variant >> 16) & 0xff, cta_req = (variant >> 24) & 0xf;
+        const int parts_code = (variant >> 28) & 0x7, parts_req = parts_code ? 1 << (parts_code - 1) : 0;
+        const int mixi = prm.mix ? 1 : 0;
+        const int D = (K + kBlk - 1) / kBlk;
+        const long long p_base = p_begin / kBlk * kBlk;
+        const bool split = (variant & BAS_RENDER_SPLIT) || (prm.mix && !(variant & BAS_RENDER_NO_SPLIT));
+        const bool can_split = split && workspace_dev != nullptr;
+        const TiledShape* best = nullptr;
+        int best_parts = 0;
+        double best_cost = 0.0;
+        for (int tu = 0; tu < 3; ++tu) {
+            int n_shapes = 0;
+            const TiledShape* shapes = tu == 0 ? tiled_shapes_tw4(&n_shapes) : tu == 1 ? tiled_shapes_tw6(&n_shapes) : tiled_shapes_tw8(&n_shapes);
+            for (int i = 0; i < n_shapes; ++i) {
+                const TiledShape& sh = shapes[i];
+                if ((tw_req && sh.tw != tw_req) || (ns_req && sh.ns != ns_req) || (cta_req && sh.minb != cta_req)) continue;
+                for (int parts = 1; parts <= sh.tw && parts <= 8; ++parts) {
+                    if (sh.tw % parts || (parts_req && parts != parts_req)) continue;
+                    if (!parts_req && parts > D) continue;                  // nothing left to share
+                    const int ctas = sh.ctas_per_sm[mixi](K, C, prm.pitch, parts);
+                    if (ctas < 1) continue;
+                    // Measured on B200 (tools/tune_render.py): every shape that keeps 8 or 12 warps per SM
+                    // busy lands within a few per cent; what separates them is how evenly the tiles of
+                    // this launch fill the device.  cost = waves of tiles x blocks a warp runs per tile x
+                    // warps that share a scheduler's FMA pipe, with small measured preferences on top.
+                    const int ts = sh.tw / parts;
+                    const double tiles = (double)bas_ceil_div(prm.p_end - p_base, (long long)ts * 1024) * (prm.mix ? 1 : n_src);
+                    const double slots = (double)device_sm_count() * ctas;
+                    const double blocks_per_tile = (double)((D + parts - 1) / parts) * (prm.mix ? n_src : 1);
+                    double waves = tiles / slots;
+                    if (!(can_split && waves > 1.0)) {
+                        // whole tiles, dealt round-robin; the last wave only occupies part of every SM and
+                        // its CTAs then run with fewer neighbours on the FMA pipe
+                        const double full = (double)(long long)waves, rest = waves - full;
+                        waves = full + (rest > 0.0 ? (rest * ctas <= 1.0 ? 1.0 / ctas + 0.25 : rest * ctas <= 2.0 ? 2.0 / ctas + 0.15 : 1.0) : 0.0);
+                    }
+                    const int wps = (ctas * sh.tw + 3) / 4;
+                    double cost = waves * blocks_per_tile * wps;
+                    cost *= 1.0 + 0.08 * (parts - 1) + (sh.ns == 1 && ctas == 1 ? 0.02 : 0.0) + (wps < 2 ? 0.3 : 0.0) +
+                            (prm.mix ? (sh.tw == 8 ? 0.0 : 0.01) : (sh.tw == 4 ? 0.0 : 0.05));
+                    if (!best || cost < best_cost) { best = &sh; best_parts = parts; best_cost = cost; }
+                }
+            }
         }
         int rc = BAS_E_UNSUPPORTED;
-        if (best_warps > 0) {
-            // Splitting tiles between CTAs pays when a tile carries many sources (mixing); with one
-            // source per tile whole tiles dealt round-robin measured faster (fewer, longer items).
-            float* ws = reinterpret_cast<float*>(workspace_dev);
-            const bool split = (variant & BAS_RENDER_SPLIT) || (prm.mix && !(variant & BAS_RENDER_NO_SPLIT));
-#define BAS_L(TW_, NS_) if (best.tw == TW_ && best.ns == NS_) rc = prm.mix ? launch_tiled<TW_, true, NS_>(prm, split, ws, workspace_bytes, st) : launch_tiled<TW_, false, NS_>(prm, split, ws, workspace_bytes, st)
-            BAS_L(2, 1); BAS_L(2, 2); BAS_L(4, 1); BAS_L(4, 2); BAS_L(8, 1); BAS_L(8, 2);
-#undef BAS_L
-        }
+        if (best) rc = best->launch[mixi](prm, best_parts, split, reinterpret_cast<float*>(workspace_dev), workspace_bytes, st);
         if (rc != BAS_E_UNSUPPORTED || base == BAS_RENDER_TILED) {
-            if (rc == BAS_E_UNSUPPORTED) bas_set_error("bas_render: no tile shape fits K=%d C=%d (requested TW=%d NS=%d)", K, C, tw_req, ns_req);
+            if (rc == BAS_E_UNSUPPORTED && !best)
+                bas_set_error("bas_render: no tile shape fits K=%d C=%d (requested TW=%d NS=%d CTAs/SM=%d parts=%d)", K, C, tw_req, ns_req, cta_req, parts_req);
             return rc;
         }
     }
@@ -200,8 +211,8 @@ extern "C" int bas_render(const float* x_dev, long long x_stride, long long n_va
 }
 
 extern "C" long long bas_render_workspace_bytes(void) {
-    // resident warps x 2 slots x (1024 outputs x 2 ears) floats, whatever the tile shape
-    return (long long)device_sm_count() * 8 * 2 * (2LL * kWarpTile) * 4;
+    // resident warps (at most 16 per SM) x 2 slots x (1024 outputs x 2 ears) floats, whatever the tile shape
+    return (long long)device_sm_count() * 16 * 2 * (2LL * kWarpTile) * 4;
 }
 
 extern "C" int bas_peak(const float* v_dev, long long n, float* peak_dev, void* stream) {

@@ -18,6 +18,7 @@ struct RenderParams {
     int mix;
     float* peaks;
     long long tiles;               // tiled kernel: tiles per source
+    int parts;                     // tiled kernel: warps that share one 1024-output stripe (split along the taps)
 };
 
 __device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
@@ -50,6 +51,11 @@ __device__ __forceinline__ void fma2_acc(u64& d, u64 a, u64 b) {          // d +
 __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
     u64 d;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
 __device__ __forceinline__ u64 sub2(u64 a, u64 b) {
@@ -98,10 +104,11 @@ struct TileGeom {
     unsigned x_bytes, f_bytes, stage_bytes, warp_x_bytes;
 };
 
-__host__ __device__ inline TileGeom tile_geom(int K, int C, int pitch, int TW) {
+// TS = stripes (1024 outputs each) per tile = warps per CTA / warps per stripe
+__host__ __device__ inline TileGeom tile_geom(int K, int C, int pitch, int TS) {
     TileGeom g;
     g.D = (K + kBlk - 1) / kBlk;
-    g.x_rows = TW * 32 + g.D;
+    g.x_rows = TS * 32 + g.D;
     g.f_rows = (g.x_rows * kBlk + C - 1) / C + 2;
     g.w_rows = 32 + g.D;
     g.x_bytes = (unsigned)g.x_rows * kBlk * 4;            // staged linearly (one bulk copy)
@@ -110,52 +117,62 @@ __host__ __device__ inline TileGeom tile_geom(int K, int C, int pitch, int TW) {
     g.warp_x_bytes = (unsigned)g.w_rows * kXPitch * 4;    // per-warp copy on the conflict-free pitch
     return g;
 }
-__host__ __device__ inline size_t tile_smem_bytes(const TileGeom& g, int TW, int NS) {
-    return 64 + (size_t)NS * g.stage_bytes + (size_t)TW * g.warp_x_bytes;
-}
 constexpr size_t kBarBytes = 64;         // full + empty mbarriers of up to 2 stages, padded
+constexpr size_t kStripeBytes = (size_t)kWarpTile * 8;      // one stripe of {L,R} partial sums
+// barriers | NS stages | per-warp input rows | blend weights per subchunk | partial sums of the warps
+// that share a stripe (parts > 1) | mix accumulators (MIX, one stripe per part-0 warp)
+__host__ __device__ inline size_t tile_smem_bytes(const TileGeom& g, int TW, int NS, int parts, int C, bool mix) {
+    const int TS = TW / parts;
+    return kBarBytes + (size_t)NS * g.stage_bytes + (size_t)TW * g.warp_x_bytes + (size_t)((C / kBlk * 4 + 15) / 16 * 16) +
+           (parts > 1 ? (size_t)(TW - TS) * kStripeBytes : 0) + (mix ? (size_t)TS * kStripeBytes : 0);
+}
 
-// One 32x32 block: acc[r] += x_sel[m] * w[(r - m) & 31] for both ears, where ring slot j holds
-//   tap (base_a + j)        of the blend of rows (ra, ra + pitch)   for j = r - m >= 0   (x from xa)
-//   tap (base_b + j - 32)   of the blend of rows (rb, rb + pitch)   for j - 32 = r - m < 0 (x from xb)
+// One 32x32 block, visited diagonal by diagonal:  acc[r] += x_sel[m] * tap(r - m)  for r, m = 0..31 with
+//   tap(j) = tap (base_a + j) of the blend of rows (ra, ra + pitch), x from xa,   for j = r - m >= 0
+//   tap(j) = tap (base_b + j) of the blend of rows (rb, rb + pitch), x from xb,   for j = r - m <  0
 // ra/rb point at tap base_a / base_b of the lane's filter row (float2 {L,R} entries, 16-byte aligned).
 // For a full block (a, b) are the same filter and base_b = base_a; for the folded first/last block
 // a is the d = 0 filter (base 0) and b the d = D filter (base 32 D).
-__device__ __forceinline__ void block_32x32(u64 (&acc)[kBlk], const float2* __restrict__ ra, u64 alpha_a,
-                                            const float2* __restrict__ rb, u64 alpha_b, int pitch,
-                                            const float* __restrict__ xa, const float* __restrict__ xb) {
-    u64 w[kBlk];
-#pragma unroll
-    for (int j = 0; j < kBlk; j += 2) {
-        const ulonglong2 h0 = *reinterpret_cast<const ulonglong2*>(ra + j);
-        const ulonglong2 h1 = *reinterpret_cast<const ulonglong2*>(ra + pitch + j);
-        w[j] = fma2(alpha_a, sub2(h1.x, h0.x), h0.x);          // H_i + alpha (H_{i+1} - H_i)   apply_hrtf.py:443
-        w[j + 1] = fma2(alpha_a, sub2(h1.y, h0.y), h0.y);
-    }
-    u64 pending = 0ull;
+// One blended tap pair {L,R} is live at a time and feeds the 32 - |j| packed FMAs of its diagonal
+// (register-reuse operand); the lane's 32 input samples sit in registers as the scalar-broadcast
+// operand.  No tap ring: 64 accumulator + 32 sample registers, and the loads and blends of the next
+// diagonal overlap the FMAs of the current one, so a block has no serial prologue.
+__device__ __forceinline__ void block_diag(u64 (&acc)[kBlk], const float2* __restrict__ ra, u64 alpha_a,
+                                           const float2* __restrict__ rb, u64 alpha_b, int pitch,
+                                           const float* __restrict__ xa, const float* __restrict__ xb) {
+    float x[kBlk];
 #pragma unroll
     for (int m4 = 0; m4 < kBlk / 4; ++m4) {
-        const float4 xav = *reinterpret_cast<const float4*>(xa + 4 * m4);
-        const float4 xbv = *reinterpret_cast<const float4*>(xb + 4 * m4);
-        const float xas[4] = {xav.x, xav.y, xav.z, xav.w};
-        const float xbs[4] = {xbv.x, xbv.y, xbv.z, xbv.w};
+        const float4 v = *reinterpret_cast<const float4*>(xa + 4 * m4);
+        x[4 * m4] = v.x; x[4 * m4 + 1] = v.y; x[4 * m4 + 2] = v.z; x[4 * m4 + 3] = v.w;
+    }
 #pragma unroll
-        for (int mm = 0; mm < 4; ++mm) {
-            const int m = m4 * 4 + mm;
-            if (m > 0) {
-                if (m & 1) {          // taps (base_b - m - 1, base_b - m) in one 16-byte load
-                    const ulonglong2 h0 = *reinterpret_cast<const ulonglong2*>(rb - m - 1);
-                    const ulonglong2 h1 = *reinterpret_cast<const ulonglong2*>(rb + pitch - m - 1);
-                    w[(kBlk - m) & 31] = fma2(alpha_b, sub2(h1.y, h0.y), h0.y);
-                    pending = fma2(alpha_b, sub2(h1.x, h0.x), h0.x);
-                } else {
-                    w[(kBlk - m) & 31] = pending;
-                }
-            }
-            const u64 xxa = pack2(xas[mm], xas[mm]);
-            const u64 xxb = pack2(xbs[mm], xbs[mm]);
+    for (int j = 0; j < kBlk; j += 2) {          // diagonals j, j + 1 >= 0: taps (base_a + j, base_a + j + 1) in one 16-byte load
+        const ulonglong2 h0 = *reinterpret_cast<const ulonglong2*>(ra + j);
+        const ulonglong2 h1 = *reinterpret_cast<const ulonglong2*>(ra + pitch + j);
+        const u64 w0 = fma2(alpha_a, sub2(h1.x, h0.x), h0.x);          // H_i + alpha (H_{i+1} - H_i)   apply_hrtf.py:443
+        const u64 w1 = fma2(alpha_a, sub2(h1.y, h0.y), h0.y);
 #pragma unroll
-            for (int r = 0; r < kBlk; ++r) fma2_acc(acc[r], r >= m ? xxa : xxb, w[(r - m) & 31]);
+        for (int m = 0; m + j < kBlk; ++m) fma2_acc(acc[m + j], pack2(x[m], x[m]), w0);
+#pragma unroll
+        for (int m = 0; m + j + 1 < kBlk; ++m) fma2_acc(acc[m + j + 1], pack2(x[m], x[m]), w1);
+    }
+#pragma unroll
+    for (int m4 = 0; m4 < kBlk / 4; ++m4) {      // folded block: the d = D part reads another input row
+        const float4 v = *reinterpret_cast<const float4*>(xb + 4 * m4);
+        x[4 * m4] = v.x; x[4 * m4 + 1] = v.y; x[4 * m4 + 2] = v.z; x[4 * m4 + 3] = v.w;
+    }
+#pragma unroll
+    for (int i = 1; i < kBlk; i += 2) {          // diagonals -i, -(i + 1): taps (base_b - i - 1, base_b - i) in one 16-byte load
+        const ulonglong2 h0 = *reinterpret_cast<const ulonglong2*>(rb - i - 1);
+        const ulonglong2 h1 = *reinterpret_cast<const ulonglong2*>(rb + pitch - i - 1);
+        const u64 w1 = fma2(alpha_b, sub2(h1.y, h0.y), h0.y);          // tap base_b - i
+#pragma unroll
+        for (int m = i; m < kBlk; ++m) fma2_acc(acc[m - i], pack2(x[m], x[m]), w1);
+        if (i + 1 < kBlk) {
+            const u64 w0 = fma2(alpha_b, sub2(h1.x, h0.x), h0.x);      // tap base_b - i - 1
+#pragma unroll
+            for (int m = i + 1; m < kBlk; ++m) fma2_acc(acc[m - i - 1], pack2(x[m], x[m]), w0);
         }
     }
 }
@@ -184,48 +201,75 @@ struct Item {
     int slot;               // workspace slot: 0 = group began in the previous CTA, 1 = continues in the next
 };
 
-template <int TW, bool MIX, int NS>
-__global__ void __launch_bounds__(TW * 32, 1)
+__device__ __forceinline__ void cta_barrier(int threads) {
+    asm volatile("bar.sync 1, %0;" ::"r"(threads) : "memory");
+}
+
+// TW warps per CTA, NS pipeline stages, MINB resident CTAs per SM the register budget is cut for.
+// prm.parts (a divisor of TW) warps share each 1024-output stripe of a tile, each running its share of
+// the item's tap blocks; their partial sums meet in shared memory in a fixed order.  A tile is then
+// TW / parts stripes: smaller tiles and more of them, which is what fills the last wave of a launch
+// whose tile count is a small multiple of the resident warps.
+template <int TW, bool MIX, int NS, int MINB>
+__global__ void __launch_bounds__(TW * 32, MINB)
 bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ workspace) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const TileGeom g = tile_geom(prm.K, prm.C, prm.pitch, TW);
+    const int P = prm.parts, TS = TW / P;
+    const TileGeom g = tile_geom(prm.K, prm.C, prm.pitch, TS);
     u64* full_bar = reinterpret_cast<u64*>(smem);              // [NS]
     u64* empty_bar = full_bar + NS;                       // [NS]
     unsigned char* stage_base = smem + kBarBytes;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float* xw = reinterpret_cast<float*>(stage_base + (size_t)NS * g.stage_bytes + (size_t)warp * g.warp_x_bytes);
-    const long long p_base = prm.p_begin / kBlk * kBlk;
+    const int stripe = warp / P, part = warp - stripe * P;     // warps of a stripe are neighbours
     const int spc = prm.C / kBlk;                              // subchunks per chunk
+    unsigned char* after_stages = stage_base + (size_t)NS * g.stage_bytes;
+    float* xw = reinterpret_cast<float*>(after_stages + (size_t)warp * g.warp_x_bytes);
+    float* alpha_tab = reinterpret_cast<float*>(after_stages + (size_t)TW * g.warp_x_bytes);
+    unsigned char* after_alpha = reinterpret_cast<unsigned char*>(alpha_tab) + (spc * 4 + 15) / 16 * 16;
+    // partial sums of parts 1..P-1 of every stripe: [stripe][part - 1][r][lane] {L,R}
+    u64* red = reinterpret_cast<u64*>(after_alpha);
+    u64* mixbuf = reinterpret_cast<u64*>(after_alpha + (P > 1 ? (size_t)(TW - TS) * kStripeBytes : 0)) + (size_t)stripe * kWarpTile;
+    const long long p_base = prm.p_begin / kBlk * kBlk;
+    const int T = TS * kWarpTile;                              // outputs per tile
     const long long n_chunks = prm.n_in / prm.C;
     // split: contiguous slice span [i0, i1);  otherwise whole groups, dealt round-robin (group = c + k G)
     const long long i0 = sp.split ? span_begin(sp, blockIdx.x, gridDim.x) : 0;
     const long long i1 = sp.split ? span_begin(sp, blockIdx.x + 1, gridDim.x) : 0;
     const long long g_first = i0 / sp.gs;
     const long long my_groups = blockIdx.x < sp.n_groups ? (sp.n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const long long n_items = sp.split ? (i1 <= i0 ? 0 : (MIX ? i1 - i0 : (i1 - 1) / sp.gs - g_first + 1))
-                                       : my_groups * (MIX ? sp.gs : 1);
+    const int n_items = (int)(sp.split ? (i1 <= i0 ? 0 : (MIX ? i1 - i0 : (i1 - 1) / sp.gs - g_first + 1))
+                                       : my_groups * (MIX ? sp.gs : 1));
+    const unsigned first_slice = (unsigned)(i0 - g_first * sp.gs);   // split: offset of the span inside its first group
 
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, TW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    for (int s = tid; s < spc; s += TW * 32) alpha_tab[s] = (float)(s * kBlk) / (float)prm.C;      // apply_hrtf.py:442
     __syncthreads();
 
-    // item j of this CTA
-    auto item_info = [&](long long j) {
+    // item j of this CTA (32-bit arithmetic: the host keeps slice counts below 2^31)
+    auto item_info = [&](int j) {
         Item it;
         long long grp; int a, b;
         if (sp.split) {
-            grp = MIX ? (i0 + j) / sp.gs : g_first + j;
+            if (MIX) {
+                const unsigned s_abs = first_slice + (unsigned)j;          // slices since the start of group g_first
+                const unsigned gi = s_abs / (unsigned)sp.gs;
+                grp = g_first + gi;
+                it.src = (int)(s_abs - gi * (unsigned)sp.gs);
+            } else {
+                grp = g_first + j;
+                it.src = 0;
+            }
             const long long lo = grp * sp.gs;
             a = (int)((i0 > lo ? i0 : lo) - lo); b = (int)((i1 < lo + sp.gs ? i1 : lo + sp.gs) - lo);
-            it.src = MIX ? (int)(i0 + j - lo) : 0;
         } else {
-            const long long k = MIX ? j / sp.gs : j;
-            grp = blockIdx.x + k * gridDim.x;
+            const unsigned k = MIX ? (unsigned)j / (unsigned)sp.gs : (unsigned)j;
+            grp = blockIdx.x + (long long)k * gridDim.x;
             a = 0; b = sp.gs;
-            it.src = MIX ? (int)(j - k * sp.gs) : 0;
+            it.src = MIX ? (int)((unsigned)j - k * (unsigned)sp.gs) : 0;
         }
         it.partial = a > 0 || b < sp.gs;
         it.slot = a > 0 ? 0 : 1;
@@ -234,7 +278,8 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
             it.d0 = 0; it.d1 = g.D;
             it.group_end = it.src == b - 1;
         } else {
-            it.src = (int)(grp / prm.tiles); it.tile = grp - (long long)it.src * prm.tiles;
+            const unsigned ug = (unsigned)grp, ut = (unsigned)prm.tiles;
+            it.src = (int)(ug / ut); it.tile = (long long)(ug - (unsigned)it.src * ut);
             it.d0 = a; it.d1 = b;
             it.group_end = true;
         }
@@ -242,27 +287,30 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
     };
     // chunk range whose filter rows a tile needs (clamped to the signal)
     auto tile_chunks = [&](long long tile, long long& n_lo, long long& c_first, int& n_rows) {
-        const long long P0 = p_base + tile * (TW * kWarpTile);
+        const long long P0 = p_base + tile * T;
         n_lo = P0 - (long long)kBlk * g.D;
-        c_first = n_lo < 0 ? 0 : n_lo / prm.C;
-        long long c_last = (P0 + (long long)TW * kWarpTile - 1) / prm.C;
+        if (n_lo < 0) c_first = 0;
+        else if (n_lo < 0x7fffffffLL) c_first = (long long)((unsigned)n_lo / (unsigned)prm.C);
+        else c_first = n_lo / prm.C;
+        const long long p_last = P0 + T - 1;
+        long long c_last = p_last < 0x7fffffffLL ? (long long)((unsigned)p_last / (unsigned)prm.C) : p_last / prm.C;
         if (c_last > n_chunks - 1) c_last = n_chunks - 1;
         if (c_first > c_last) c_first = c_last;
         n_rows = (int)(c_last - c_first + 2);                   // + the boundary after the last chunk
     };
 
     // ---- producer: warp 0 stages item j into ring slot j % NS --------------------------------
-    auto produce = [&](long long j) {
-        const int st = (int)(j % NS);
-        const long long use = j / NS;
+    auto produce = [&](int j) {
+        const int st = j % NS;
+        const int use = j / NS;
         if (use > 0) mbar_wait(empty_bar + st, (unsigned)((use - 1) & 1));      // consumers left the slot
-        const Item it = item_info(j);
-        long long n_lo, c_first; int n_rows;
-        tile_chunks(it.tile, n_lo, c_first, n_rows);
-        float* xs = reinterpret_cast<float*>(stage_base + (size_t)st * g.stage_bytes);
-        float2* fs = reinterpret_cast<float2*>(stage_base + (size_t)st * g.stage_bytes + g.x_bytes);
-        const float* x = prm.x + (long long)it.src * prm.x_stride;
         if (lane == 0) {
+            const Item it = item_info(j);
+            long long n_lo, c_first; int n_rows;
+            tile_chunks(it.tile, n_lo, c_first, n_rows);
+            float* xs = reinterpret_cast<float*>(stage_base + (size_t)st * g.stage_bytes);
+            float2* fs = reinterpret_cast<float2*>(stage_base + (size_t)st * g.stage_bytes + g.x_bytes);
+            const float* x = prm.x + (long long)it.src * prm.x_stride;
             // two bulk copies per item: the in-range part of the input span, and the filter rows.
             // Samples outside [0, n_valid) are never copied; consumers zero them while re-laying out.
             const long long na = n_lo < 0 ? 0 : n_lo;
@@ -280,38 +328,40 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
     if (warp == 0 && n_items > 0) produce(0);
 
     u64 acc[kBlk];
-    u64 mixacc[MIX ? kBlk : 1];
 #pragma unroll
     for (int r = 0; r < kBlk; ++r) acc[r] = 0ull;
-    if (MIX) {
+    if (MIX && part == 0) {
 #pragma unroll
-        for (int r = 0; r < (MIX ? kBlk : 1); ++r) mixacc[r] = 0ull;
+        for (int r = 0; r < kBlk; ++r) mixbuf[r * 32 + lane] = 0ull;
     }
-    const int blk = warp * 32 + lane;                           // output block of this lane inside the tile
+    const int blk = stripe * 32 + lane;                         // output block of this lane inside the tile
     const bool vec_ok = (prm.p_begin & 3) == 0 && (prm.out_stride & 3) == 0 &&
                         (reinterpret_cast<uintptr_t>(prm.out) & 15) == 0;
 
-    for (long long j = 0; j < n_items; ++j) {
+    for (int j = 0; j < n_items; ++j) {
         // two stages: the copy of item j+1 overlaps the arithmetic of item j.  One stage: the slot can
         // only be refilled after every warp (this one included) has left it - see below.
         if (NS > 1 && warp == 0 && j + 1 < n_items) produce(j + 1);
-        const int st = (int)(j % NS);
+        const int st = j % NS;
         const Item it = item_info(j);
         long long n_lo, c_first; int n_rows;
         tile_chunks(it.tile, n_lo, c_first, n_rows);
-        const long long P0 = p_base + it.tile * (TW * kWarpTile);
-        const bool warp_live = P0 + (long long)warp * kWarpTile < prm.p_end;
+        const long long P0 = p_base + it.tile * T;
+        const bool warp_live = P0 + (long long)stripe * kWarpTile < prm.p_end;
         const float* xs = reinterpret_cast<const float*>(stage_base + (size_t)st * g.stage_bytes);
         const float2* fs = reinterpret_cast<const float2*>(stage_base + (size_t)st * g.stage_bytes + g.x_bytes);
         const long long q0 = n_lo / kBlk;                       // exact (n_lo % 32 == 0), may be negative
+        // this warp's share of the item's tap blocks
+        const int len = it.d1 - it.d0;
+        const int d_first = it.d0 + (len * part) / P, d_last = it.d0 + (len * (part + 1)) / P;
 
         mbar_wait(full_bar + st, (unsigned)((j / NS) & 1));
 
-        if (warp_live) {
+        if (warp_live && d_last > d_first) {
             // re-lay this warp's input rows from the linear staging buffer onto the 144-byte pitch
             // (lane-per-row reads below are then conflict free) and zero what lies outside the signal
-            const long long n_w = n_lo + (long long)warp * kWarpTile;
-            const float4* lin = reinterpret_cast<const float4*>(xs) + warp * (kWarpTile / 4);
+            const long long n_w = n_lo + (long long)stripe * kWarpTile;
+            const float4* lin = reinterpret_cast<const float4*>(xs) + stripe * (kWarpTile / 4);
             for (int idx = lane; idx < g.w_rows * 8; idx += 32) {
                 const int row = idx >> 3, ch = idx & 7;
                 const long long n = n_w + (long long)row * kBlk + ch * 4;
@@ -320,52 +370,68 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
                 *reinterpret_cast<float4*>(xw + row * kXPitch + ch * 4) = v;
             }
             __syncwarp();
-        }
-        if (warp_live) {
             // Filter row (chunk) and blend weight of the lane's input row.  Input rows are visited in
             // descending order (xrow = blk + D - d), so (chunk, sub) is divided once per item and then
             // stepped; rows outside the staged range belong to input rows that are all zero (clamped).
             const int q_top = (int)q0 + blk + g.D;               // absolute subchunk of the d = 0 row
             const int cf = (int)c_first;
-            int chunk_a = q_top < 0 ? 0 : q_top / spc;
-            int sub_a = q_top < 0 ? 0 : q_top - chunk_a * spc;
-            auto row_of = [&](int chunk, const float2*& rowp) {
+            auto split_q = [&](int q, int& chunk, int& sub) {
+                if (q < 0) { chunk = 0; sub = 0; }
+                else { chunk = (int)((unsigned)q / (unsigned)spc); sub = q - chunk * spc; }
+            };
+            auto row_of = [&](int chunk) {
                 int ri = chunk - cf;
                 ri = ri < 0 ? 0 : (ri > n_rows - 2 ? n_rows - 2 : ri);
-                rowp = fs + ri * prm.pitch;
+                return fs + ri * prm.pitch;
             };
-            // d = 0 is the folded block: ring initialised from the d = 0 filter (r >= m), refilled from
-            // the d = D filter (r < m).  One call site keeps the unrolled body in the instruction cache.
+            int chunk, sub;
+            split_q(q_top - d_first, chunk, sub);
+            // d = 0 is the folded block: diagonals >= 0 from the d = 0 filter, diagonals < 0 from the
+            // d = D filter.  One call site keeps the unrolled body in the instruction cache.
 #pragma unroll 1
-            for (int d = it.d0; d < it.d1; ++d) {
-                // (chunk, sub) of row q_top - d
-                int chunk = chunk_a, sub = sub_a - d;
-                if (q_top - d < 0) { chunk = 0; sub = 0; }
-                else { while (sub < 0) { sub += spc; --chunk; } }
-                const float2 *ra, *rb;
-                row_of(chunk, ra);
-                ra += kBlk * d;
-                const float alpha = (float)(sub * kBlk) / (float)prm.C;          // apply_hrtf.py:442
+            for (int d = d_first; d < d_last; ++d) {
+                const float2* ra = row_of(chunk) + kBlk * d;
+                const float alpha = alpha_tab[sub];
                 u64 aa = pack2(alpha, alpha), ab = aa;
-                rb = ra;
+                const float2* rb = ra;
                 const int xrow_a = blk + g.D - d;
                 int xrow_b = xrow_a;
                 if (d == 0) {
                     xrow_b = blk;
-                    const int qb = q_top - g.D;
-                    const int chunk_b = qb < 0 ? 0 : qb / spc;
-                    const int sub_b = qb < 0 ? 0 : qb - chunk_b * spc;
-                    row_of(chunk_b, rb);
-                    rb += kBlk * g.D;
-                    const float alpha_b = (float)(sub_b * kBlk) / (float)prm.C;
+                    int chunk_b, sub_b;
+                    split_q(q_top - g.D, chunk_b, sub_b);
+                    rb = row_of(chunk_b) + kBlk * g.D;
+                    const float alpha_b = alpha_tab[sub_b];
                     ab = pack2(alpha_b, alpha_b);
                 }
-                block_32x32(acc, ra, aa, rb, ab, prm.pitch, xw + (xrow_a - warp * 32) * kXPitch, xw + (xrow_b - warp * 32) * kXPitch);
+                block_diag(acc, ra, aa, rb, ab, prm.pitch, xw + (xrow_a - stripe * 32) * kXPitch, xw + (xrow_b - stripe * 32) * kXPitch);
+                // next row down: q - 1
+                if (q_top - d - 1 < 0) { chunk = 0; sub = 0; }
+                else if (--sub < 0) { sub = spc - 1; --chunk; }
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty_bar + st);             // this warp is done with the slot
         if (NS == 1 && warp == 0 && j + 1 < n_items) produce(j + 1);
+
+        // ---- the warps of a stripe add up: parts 1.. hand their sums to part 0, fixed order ---------
+        if (P > 1) {
+            if (part > 0) {
+                u64* dst = red + ((size_t)(stripe * (P - 1) + part - 1) * kBlk) * 32 + lane;
+#pragma unroll
+                for (int r = 0; r < kBlk; ++r) { dst[r * 32] = acc[r]; acc[r] = 0ull; }
+            }
+            cta_barrier(TW * 32);
+            if (part == 0) {
+                for (int pp = 0; pp < P - 1; ++pp) {
+                    const u64* srcp = red + ((size_t)(stripe * (P - 1) + pp) * kBlk) * 32 + lane;
+#pragma unroll
+                    for (int r = 0; r < kBlk; ++r) acc[r] = add2(acc[r], srcp[r * 32]);
+                }
+            }
+            cta_barrier(TW * 32);                               // red may be overwritten by the next item
+            if (part > 0) continue;
+        }
 
         // ---- peak, gain, mix, store ----------------------------------------------------------------
         const long long pb = P0 + (long long)blk * kBlk;        // first output of this lane
@@ -381,21 +447,28 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
             if (lane == 0 && pk > 0.f) atomic_max_nonneg(prm.peaks + it.src, pk);
         }
         if (MIX) {
+            // gain-weighted running sum over the sources of the tile, kept in shared memory; the last
+            // source of the group leaves the total in acc
             const u64 g2 = pack2(gain, gain);
+            const bool first_src = it.src == 0 || j == 0;
 #pragma unroll
-            for (int r = 0; r < kBlk; ++r) { mixacc[r & (MIX ? 31 : 0)] = fma2(g2, acc[r], mixacc[r & (MIX ? 31 : 0)]); acc[r] = 0ull; }
+            for (int r = 0; r < kBlk; ++r) {
+                const u64 prev = first_src ? 0ull : mixbuf[r * 32 + lane];
+                acc[r] = fma2(g2, acc[r], prev);
+                if (!it.group_end) { mixbuf[r * 32 + lane] = acc[r]; acc[r] = 0ull; }
+            }
         }
         if (it.group_end) {
             if (it.partial) {
-                // partial tile -> workspace[cta][slot][ear][TW*1024], no gain (one source per tile) / mixed
-                float* w = workspace + ((long long)blockIdx.x * 2 + it.slot) * (2 * TW * kWarpTile) + blk * kBlk;
+                // partial tile -> workspace[cta][slot][ear][T], no gain (one source per tile) / mixed
+                float* w = workspace + ((long long)blockIdx.x * 2 + it.slot) * (2 * T) + blk * kBlk;
 #pragma unroll
                 for (int r4 = 0; r4 < kBlk; r4 += 4) {
                     float l[4], rr[4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) unpack2(MIX ? mixacc[(r4 + i) & (MIX ? 31 : 0)] : acc[r4 + i], l[i], rr[i]);
+                    for (int i = 0; i < 4; ++i) unpack2(acc[r4 + i], l[i], rr[i]);
                     *reinterpret_cast<float4*>(w + r4) = make_float4(l[0], l[1], l[2], l[3]);
-                    *reinterpret_cast<float4*>(w + TW * kWarpTile + r4) = make_float4(rr[0], rr[1], rr[2], rr[3]);
+                    *reinterpret_cast<float4*>(w + T + r4) = make_float4(rr[0], rr[1], rr[2], rr[3]);
                 }
             } else {
                 float* o = prm.out + (MIX ? 0 : (long long)it.src * 2 * prm.out_stride);
@@ -406,7 +479,7 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
                         float l[4], rr[4];
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            unpack2(MIX ? mixacc[(r4 + i) & (MIX ? 31 : 0)] : acc[r4 + i], l[i], rr[i]);
+                            unpack2(acc[r4 + i], l[i], rr[i]);
                             if (!MIX) { l[i] *= gain; rr[i] *= gain; }
                         }
                         *reinterpret_cast<float4*>(o + off + r4) = make_float4(l[0], l[1], l[2], l[3]);
@@ -415,7 +488,7 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
                 } else {
 #pragma unroll
                     for (int r = 0; r < kBlk; ++r) {
-                        float l, rr; unpack2(MIX ? mixacc[r & (MIX ? 31 : 0)] : acc[r], l, rr);
+                        float l, rr; unpack2(acc[r], l, rr);
                         if (!MIX) { l *= gain; rr *= gain; }
                         if (pb + r >= prm.p_begin && pb + r < prm.p_end) { o[off + r] = l; o[prm.out_stride + off + r] = rr; }
                     }
@@ -423,10 +496,6 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
             }
 #pragma unroll
             for (int r = 0; r < kBlk; ++r) acc[r] = 0ull;
-            if (MIX) {
-#pragma unroll
-                for (int r = 0; r < (MIX ? kBlk : 1); ++r) mixacc[r] = 0ull;
-            }
         }
     }
 }
@@ -434,13 +503,13 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
 // Adds the two partial tiles of every group a span boundary split (fixed order: the earlier CTA's
 // part first), applies the gain, takes the peak and stores.  grid = (boundaries, 2 ears, T / 1024).
 static __global__ void __launch_bounds__(256)
-bas_render_fixup_kernel(RenderParams prm, SpanInfo sp, const float* __restrict__ workspace, long long G, int TW) {
+bas_render_fixup_kernel(RenderParams prm, SpanInfo sp, const float* __restrict__ workspace, long long G, int TS) {
     const long long c = blockIdx.x + 1;                           // boundary between CTA c-1 and CTA c
     const int ear = blockIdx.y;
     const long long ic = span_begin(sp, c, G);
     if (ic % sp.gs == 0 || ic >= sp.total) return;                // boundary on a group edge: nothing was split
     const long long grp = ic / sp.gs;
-    const int T = TW * kWarpTile;
+    const int T = TS * kWarpTile;
     const int src = prm.mix ? 0 : (int)(grp / prm.tiles);
     const long long tile = prm.mix ? grp : grp - (long long)src * prm.tiles;
     const long long p_base = prm.p_begin / kBlk * kBlk;
@@ -477,33 +546,41 @@ inline int device_sm_count() {
     return sm_count;
 }
 
-// Resident warps per SM this shape reaches (0: does not fit).
-template <int TW, bool MIX, int NS>
-int tiled_warps_per_sm(int K, int C, int pitch) {
-    const TileGeom g = tile_geom(K, C, pitch, TW);
-    const size_t smem = tile_smem_bytes(g, TW, NS);
+// Resident CTAs per SM this shape reaches with `parts` warps per stripe (0: does not fit).
+template <int TW, bool MIX, int NS, int MINB>
+int tiled_ctas_per_sm(int K, int C, int pitch, int parts) {
+    if (parts < 1 || TW % parts) return 0;
+    const TileGeom g = tile_geom(K, C, pitch, TW / parts);
+    const size_t smem = tile_smem_bytes(g, TW, NS, parts, C, MIX);
     if (smem > 227 * 1024) return 0;
-    auto kern = bas_render_tiled_kernel<TW, MIX, NS>;
+    auto kern = bas_render_tiled_kernel<TW, MIX, NS, MINB>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TW * 32, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
-    return per_sm * TW;
+    return per_sm;
 }
 
-template <int TW, bool MIX, int NS>
-int launch_tiled(RenderParams prm, bool want_split, float* workspace, long long workspace_bytes, cudaStream_t st) {
-    const TileGeom g = tile_geom(prm.K, prm.C, prm.pitch, TW);
-    const size_t smem = tile_smem_bytes(g, TW, NS);
+template <int TW, bool MIX, int NS, int MINB>
+int launch_tiled(RenderParams prm, int parts, bool want_split, float* workspace, long long workspace_bytes, cudaStream_t st) {
+    if (parts < 1 || TW % parts) return BAS_E_UNSUPPORTED;
+    const int TS = TW / parts;
+    const TileGeom g = tile_geom(prm.K, prm.C, prm.pitch, TS);
+    const size_t smem = tile_smem_bytes(g, TW, NS, parts, prm.C, MIX);
     if (smem > 227 * 1024) return BAS_E_UNSUPPORTED;
-    auto kern = bas_render_tiled_kernel<TW, MIX, NS>;
+    auto kern = bas_render_tiled_kernel<TW, MIX, NS, MINB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { bas_set_error("bas_render: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     const long long p_base = prm.p_begin / kBlk * kBlk;
-    prm.tiles = bas_ceil_div(prm.p_end - p_base, (long long)TW * kWarpTile);
+    prm.parts = parts;
+    prm.tiles = bas_ceil_div(prm.p_end - p_base, (long long)TS * kWarpTile);
     SpanInfo sp;
     sp.gs = MIX ? prm.n_src : g.D;
     sp.n_groups = MIX ? prm.tiles : prm.tiles * prm.n_src;
     sp.total = sp.n_groups * sp.gs;
+    if (sp.total >= 0x7fffffffLL || prm.tiles >= 0x7fffffffLL) {
+        bas_set_error("bas_render: more than 2^31 work slices in one launch; render the signal in time ranges");
+        return BAS_E_UNSUPPORTED;
+    }
     // persistent grid: as many CTAs as the device keeps resident
     int per_sm = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TW * 32, smem);
@@ -512,39 +589,36 @@ int launch_tiled(RenderParams prm, bool want_split, float* workspace, long long 
     if (grid > sp.n_groups) grid = sp.n_groups;
     // split groups between CTAs only when every span is longer than a group (then a group has at
     // most two contributors) and the caller gave a workspace
-    const long long need = grid * 2 * (2LL * TW * kWarpTile) * 4;
+    const long long need = grid * 2 * (2LL * TS * kWarpTile) * 4;
     sp.split = (want_split && workspace && workspace_bytes >= need && grid > 1 && sp.total / grid >= sp.gs + 1) ? 1 : 0;
     kern<<<(unsigned)grid, TW * 32, smem, st>>>(prm, sp, workspace);
     e = cudaGetLastError();
     if (e != cudaSuccess) { bas_set_error("bas_render: tiled launch failed: %s", cudaGetErrorString(e)); return (int)e; }
     if (sp.split) {
-        dim3 fgrid((unsigned)(grid - 1), 2, (unsigned)TW);
-        bas_render_fixup_kernel<<<fgrid, 256, 0, st>>>(prm, sp, workspace, grid, TW);
+        dim3 fgrid((unsigned)(grid - 1), 2, (unsigned)TS);
+        bas_render_fixup_kernel<<<fgrid, 256, 0, st>>>(prm, sp, workspace, grid, TS);
         e = cudaGetLastError();
         if (e != cudaSuccess) { bas_set_error("bas_render: fix-up launch failed: %s", cudaGetErrorString(e)); return (int)e; }
     }
     return 0;
 }
 
+// One compiled tile shape: warps per CTA x pipeline stages x CTAs per SM the registers allow.
+// [0] = one source per tile, [1] = mixing.
+struct TiledShape {
+    int tw, ns, minb;
+    int (*ctas_per_sm[2])(int K, int C, int pitch, int parts);
+    int (*launch[2])(RenderParams prm, int parts, bool want_split, float* workspace, long long workspace_bytes, cudaStream_t st);
+};
+#define BAS_TILED_SHAPE(TW_, NS_, MINB_)                                                            \
+    { TW_, NS_, MINB_,                                                                              \
+      { tiled_ctas_per_sm<TW_, false, NS_, MINB_>, tiled_ctas_per_sm<TW_, true, NS_, MINB_> },      \
+      { launch_tiled<TW_, false, NS_, MINB_>, launch_tiled<TW_, true, NS_, MINB_> } }
 
-// explicit instantiations live in render_tw2.cu / render_tw4.cu / render_tw8.cu
-#define BAS_DECLARE_TILED(TW_)                                                                              \
-    extern template int launch_tiled<TW_, false, 1>(RenderParams, bool, float*, long long, cudaStream_t);    \
-    extern template int launch_tiled<TW_, false, 2>(RenderParams, bool, float*, long long, cudaStream_t);    \
-    extern template int launch_tiled<TW_, true, 1>(RenderParams, bool, float*, long long, cudaStream_t);     \
-    extern template int launch_tiled<TW_, true, 2>(RenderParams, bool, float*, long long, cudaStream_t);     \
-    extern template int tiled_warps_per_sm<TW_, false, 1>(int, int, int);                                    \
-    extern template int tiled_warps_per_sm<TW_, false, 2>(int, int, int);                                    \
-    extern template int tiled_warps_per_sm<TW_, true, 1>(int, int, int);                                     \
-    extern template int tiled_warps_per_sm<TW_, true, 2>(int, int, int);
-#define BAS_INSTANTIATE_TILED(TW_)                                                                    \
-    template int launch_tiled<TW_, false, 1>(RenderParams, bool, float*, long long, cudaStream_t);    \
-    template int launch_tiled<TW_, false, 2>(RenderParams, bool, float*, long long, cudaStream_t);    \
-    template int launch_tiled<TW_, true, 1>(RenderParams, bool, float*, long long, cudaStream_t);     \
-    template int launch_tiled<TW_, true, 2>(RenderParams, bool, float*, long long, cudaStream_t);     \
-    template int tiled_warps_per_sm<TW_, false, 1>(int, int, int);                                    \
-    template int tiled_warps_per_sm<TW_, false, 2>(int, int, int);                                    \
-    template int tiled_warps_per_sm<TW_, true, 1>(int, int, int);                                     \
-    template int tiled_warps_per_sm<TW_, true, 2>(int, int, int);
+// defined in render_tw4.cu / render_tw6.cu / render_tw8.cu (one translation unit per tile width, so
+// they compile in parallel)
+const TiledShape* tiled_shapes_tw4(int* count);
+const TiledShape* tiled_shapes_tw6(int* count);
+const TiledShape* tiled_shapes_tw8(int* count);
 
 }  // namespace bas_render_detail

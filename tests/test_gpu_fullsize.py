@@ -55,7 +55,7 @@ def test_linearity_and_tile_shape_independence(bas, synth_bank, long_render):
     x, y = long_render
     traj = [lissajous()]
     y2 = bas.render_sources((2.0 * x)[None], 512, 32, traj, synth_bank, normalise=False,
-                            variant=bas._cabi.RENDER_TILED | (2 << 8))[0]
+                            variant=bas._cabi.render_variant(tw=6, parts=2))[0]
     # scaling by 2 is exact in binary floating point; a different tile shape only changes the
     # order of partial sums
     assert rel_l2(y2, 2.0 * y) <= 1e-6

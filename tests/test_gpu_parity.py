@@ -126,20 +126,40 @@ def _shape_reference(oracle, bank, x, traj):
     return _SHAPE_REF['y']
 
 
+def _shape_reference_n(oracle, bank, x, traj, key):
+    if key not in _SHAPE_REF:
+        _SHAPE_REF[key] = oracle.make_signal_move_2d(x, 512, 32, traj, bank)
+    return _SHAPE_REF[key]
+
+
 @pytest.mark.parametrize('split', [False, True])
-@pytest.mark.parametrize('ns', [1, 2])
-@pytest.mark.parametrize('tw', [2, 4, 8])
-def test_tiled_shapes_vs_oracle(bas, oracle, synth_bank, tw, ns, split):
-    """Every compiled tile shape (warps per CTA x pipeline stages) of the register-tiled kernel,
-    with whole tiles per CTA and with tiles split between CTAs (stream-K + fix-up), K = 256."""
+@pytest.mark.parametrize('parts', [1, 2, 4])
+@pytest.mark.parametrize('shape', [(4, 2, 2), (4, 1, 2), (4, 1, 3), (6, 1, 2), (6, 2, 1), (8, 2, 1), (8, 1, 1)])
+def test_tiled_shapes_vs_oracle(bas, oracle, synth_bank, shape, parts, split):
+    """Every compiled tile shape of the register-tiled kernel (warps per CTA x pipeline stages x CTAs
+    per SM), with 1, 2 or 4 warps sharing a stripe (tap blocks split between warps, summed in shared
+    memory), with whole tiles per CTA and with tiles split between CTAs (stream-K + fix-up), K = 256."""
+    tw, ns, ctas = shape
+    if tw % parts:
+        pytest.skip('parts must divide the warps per CTA')
     rng = np.random.default_rng(5)
     n = 9000
     x = (0.05 * rng.standard_normal(n)).astype(np.float32)
     traj = _traj(3)
     want = _shape_reference(oracle, synth_bank, x, traj)
-    variant = bas._cabi.RENDER_TILED | (tw << 8) | (ns << 16) | (bas._cabi.RENDER_SPLIT if split else bas._cabi.RENDER_NO_SPLIT)
+    variant = bas._cabi.render_variant(tw, ns, ctas, parts, split)
     got = bas.render_sources(x[None], 512, 32, [traj], synth_bank, variant=variant)[0].T
     close(got, want)
+    # the same shape mixing three sources (accumulators of the mix live in shared memory)
+    xs = np.stack([x, x[::-1].copy(), 0.5 * x])
+    trajs = [traj, _traj(4), _traj(5)]
+    want_mix = sum(_shape_reference_n(oracle, synth_bank, xs[s], trajs[s], s) for s in range(3))
+    try:
+        got_mix = bas.render_sources(xs, 512, 32, trajs, synth_bank, mix=True, variant=variant)
+    except bas.BasError as e:          # the mix accumulators of this shape do not fit in shared memory
+        assert 'no tile shape fits' in str(e)
+        return
+    close(got_mix.T, want_mix)
 
 
 @pytest.mark.parametrize('k_taps,c,n', [(100, 512, 5000), (256, 128, 4000), (33, 64, 1500), (512, 512, 6000), (1, 32, 200)])
@@ -192,10 +212,15 @@ def test_time_range_windows(bas, synth_bank):
     rng = np.random.default_rng(31)
     x = (0.05 * rng.standard_normal((1, 7000))).astype(np.float32)
     traj = [_traj(4)]
-    full = bas.render_sources(x, 512, 32, traj, synth_bank, normalise=False)
-    for p0, p1 in [(0, 1), (1, 1000), (777, 4099), (4096, 7423), (7000, 7423)]:
+    for shape in (bas._cabi.render_variant(4, 1, 3, 1), bas._cabi.render_variant(8, 2, 1, 2), bas._cabi.RENDER_GENERIC):
+        full = bas.render_sources(x, 512, 32, traj, synth_bank, normalise=False, variant=shape)
+        for p0, p1 in [(0, 1), (1, 1000), (777, 4099), (4096, 7423), (7000, 7423)]:
+            part = bas.render_sources(x, 512, 32, traj, synth_bank, normalise=False, time_range=(p0, p1), variant=shape)
+            assert np.array_equal(part, full[:, :, p0:p1])      # same kernel, same order of operations
+    auto = bas.render_sources(x, 512, 32, traj, synth_bank, normalise=False)
+    for p0, p1 in [(1, 1000), (4096, 7423)]:     # the library's own choice of tile shape may differ per window
         part = bas.render_sources(x, 512, 32, traj, synth_bank, normalise=False, time_range=(p0, p1))
-        assert np.array_equal(part, full[:, :, p0:p1])      # same kernel, same order of operations
+        assert rel_l2(part, auto[:, :, p0:p1]) <= 1e-6
 
 
 def test_edge_cases(bas, oracle, golden_bank):
@@ -273,9 +298,12 @@ def test_host_pipeline_equals_device_path(bas, synth_bank, phases, seg_bytes, mo
     trajs = [vec(0), vec(1), lambda t: (np.float64(0.3 * np.cos(k * t)), np.float64((2 * k * t) % (2 * np.pi)))]
     xd = torch.zeros((n_src, (n + 511) // 512 * 512), dtype=torch.float32, device='cuda')
     xd[:, :n] = torch.from_numpy(x).cuda()
+    # one tile shape for both paths: the library otherwise picks the shape by the size of each launch,
+    # and a different shape may sum the same products in a different order
+    shape = bas._cabi.render_variant(4, 1, 2, 1, split=False)
     for mix in (False, True):
-        want, want_peaks = bas.render_sources(xd, 512, 32, trajs, synth_bank, mix=mix, return_device=True, return_peaks=True)
-        got, got_peaks = bas.render_sources(x, 512, 32, trajs, synth_bank, mix=mix, return_peaks=True)
+        want, want_peaks = bas.render_sources(xd, 512, 32, trajs, synth_bank, mix=mix, return_device=True, return_peaks=True, variant=shape)
+        got, got_peaks = bas.render_sources(x, 512, 32, trajs, synth_bank, mix=mix, return_peaks=True, variant=shape)
         assert isinstance(got, np.ndarray) and got.dtype == np.float32
         assert np.array_equal(got, want.cpu().numpy())
         assert np.array_equal(got_peaks, want_peaks) and got_peaks[1] > 1
@@ -285,6 +313,9 @@ def test_host_pipeline_equals_device_path(bas, synth_bank, phases, seg_bytes, mo
            np.stack([np.asarray(f(times)[1] if getattr(f, 'vectorized', False) else [f(int(t))[1] for t in times], dtype=np.float64) for f in trajs]),
            bas._cabi.AZ_F64)
     xp = torch.from_numpy(x).pin_memory().numpy()
-    full = bas.render_sources(xd, 512, 32, pre, synth_bank, normalise=False, return_device=True).cpu().numpy()
-    part = bas.render_sources(xp, 512, 32, pre, synth_bank, normalise=False, time_range=(12_345, 140_001))
+    full = bas.render_sources(xd, 512, 32, pre, synth_bank, normalise=False, return_device=True, variant=shape).cpu().numpy()
+    part = bas.render_sources(xp, 512, 32, pre, synth_bank, normalise=False, time_range=(12_345, 140_001), variant=shape)
     assert np.array_equal(part, full[:, :, 12_345:140_001])
+    # and with the library's own choice of shapes: same result to rounding
+    auto = bas.render_sources(xp, 512, 32, pre, synth_bank, normalise=False)
+    assert rel_l2(auto, full) <= 1e-6

@@ -24,6 +24,7 @@ def main():
     ups = int(sys.argv[3]) if len(sys.argv) > 3 else 8
     mix = int(sys.argv[4]) if len(sys.argv) > 4 else (1 if n_src > 1 else 0)
     only_tw = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+    only_names = sys.argv[6].split(',') if len(sys.argv) > 6 else None
     dev = torch.device('cuda', 0)
     f = bas.bank_synth.build_bank(ups, seed=0)
 
@@ -45,31 +46,37 @@ def main():
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
     results = {}
     workspace = _cabi.render_workspace(torch, dev)
-    for tw, ns, ts in ((0, 0, 0), (0, 0, 1), (2, 2, 0), (4, 2, 0), (8, 2, 0), (2, 2, 1), (4, 2, 1), (8, 2, 1), (4, 1, 1), (8, 1, 1), (8, 1, 0)):
-        if only_tw and (tw != only_tw or ts):
-            continue
-        variant = _cabi.RENDER_TILED | (tw << 8) | (ns << 16) | (_cabi.RENDER_NO_SPLIT if ts else _cabi.RENDER_SPLIT)
+    for (tw, ns, ctas) in ((0, 0, 0),) + tuple(_cabi.TILED_SHAPES):
+        for parts in (0, 1, 2, 4):
+            for split in ((False, True) if mix else (False,)):
+                if (tw == 0) != (parts == 0) or (tw and tw % parts):
+                    continue
+                if only_tw and tw != only_tw:
+                    continue
+                if only_names and '%dx%dx%d/p%d%s' % (tw, ns, ctas, parts, '/split' if split else '') not in only_names:
+                    continue
+                variant = _cabi.render_variant(tw, ns, ctas, parts, split)
+                name = '%dx%dx%d/p%d%s' % (tw, ns, ctas, parts, '/split' if split else '')
 
-        def run():
-            return lib.bas_render(x.data_ptr(), n_in, n_in, n_src, n_in, 512, 32, k, filt.data_ptr(), None, 0, n_out,
-                                  out.data_ptr(), out.shape[-1], mix, peaks.data_ptr(), variant, workspace.data_ptr(), workspace.numel(), stream)
-        rc = run()
-        if rc != 0:
-            results['%dx%d%s' % (tw, ns, 'nosplit' if ts else 'split')] = 'rc=%d %s' % (rc, _cabi.last_error())
-            continue
-        torch.cuda.synchronize()
-        times = []
-        for _ in range(5):
-            flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            run()
-            e1.record()
-            torch.cuda.synchronize()
-            times.append(e0.elapsed_time(e1))
-        ms = float(np.median(times))
-        results['%dx%d%s' % (tw, ns, 'nosplit' if ts else 'split')] = {'ms': round(ms, 4), 'tfma_s': round(2.0 * k * n_in * n_src / ms / 1e9, 2),
-                                        'Gpairs_s': round(n_out * n_src / ms / 1e6, 2)}
+                def run():
+                    return lib.bas_render(x.data_ptr(), n_in, n_in, n_src, n_in, 512, 32, k, filt.data_ptr(), None, 0, n_out,
+                                          out.data_ptr(), out.shape[-1], mix, peaks.data_ptr(), variant, workspace.data_ptr(), workspace.numel(), stream)
+                rc = run()
+                if rc != 0:
+                    results[name] = 'rc=%d %s' % (rc, _cabi.last_error())
+                    continue
+                torch.cuda.synchronize()
+                times = []
+                for _ in range(5):
+                    flush.zero_()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    run()
+                    e1.record()
+                    torch.cuda.synchronize()
+                    times.append(e0.elapsed_time(e1))
+                ms = float(np.median(times))
+                results[name] = {'ms': round(ms, 4), 'tfma_s': round(2.0 * k * n_in * n_src / ms / 1e9, 2), 'Gpairs_s': round(n_out * n_src / ms / 1e6, 2)}
     print(json.dumps({'seconds': seconds, 'mix': mix, 'n_src': n_src, 'K': k, 'U': ups, 'results': results}, indent=1))
 
 
