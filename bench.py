@@ -238,18 +238,22 @@ def run_ours(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, collective=True):
+        """ms per step of fn over `steps` steps after `warmup`: CUDA events on the launching stream,
+        bracketed by a barrier + synchronize, max over ranks.  collective=False: this rank only (the
+        per-kernel timings rank 0 takes for the roofline)."""
+        sync = barrier if collective else torch.cuda.synchronize
         for i in range(warmup):
             fn(sets[i % n_sets])
-        barrier()
+        sync()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
             fn(sets[(warmup + i) % n_sets])
         e1.record()
-        barrier()
+        sync()
         ms = e0.elapsed_time(e1)
-        if dist is not None:
+        if collective and dist is not None:
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t)
@@ -281,14 +285,14 @@ def run_ours(args, rank, local_rank, world):
 
     if rank == 0:
         # ---- roofline of the dominant kernel (render) -------------------------------------------
-        ms_render = timed(step_render, max(args.steps, 20), 3)
+        ms_render = timed(step_render, max(args.steps, 20), 3, collective=False)
         ms_synth = timed(lambda s: _cabi.check(lib.bas_ir_synth(bdev.bank_pp.data_ptr(), UPS, k, s['terms'].data_ptr(), n_pts,
                                                               _cabi.IR_ROWS, s['filt'].data_ptr(), k, stream), 'bas_ir_synth'),
-                         max(args.steps, 20), 3)
+                         max(args.steps, 20), 3, collective=False)
         ms_plan = timed(lambda s: _cabi.check(lib.bas_plan_build(bdev.diffs[0].data_ptr(), bdev.diffs[1].data_ptr(), UPS, k * UPS,
                                                               s['elev'].data_ptr(), s['azim'].data_ptr(), None, _cabi.AZ_F64, n_pts,
                                                               s['terms'].data_ptr(), None, s['status'].data_ptr(), stream), 'plan'),
-                        max(args.steps, 20), 3)
+                        max(args.steps, 20), 3, collective=False)
         algo_bytes = 12.0 * n_out
         peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
         if os.path.exists(peaks_path):
@@ -301,7 +305,7 @@ def run_ours(args, rank, local_rank, world):
         fma = {}
         for name, packed in (('fma_f32', 0), ('fma_f32x2', 1)):
             iters = 4096
-            ms = timed(lambda s: _cabi.check(lib.bas_probe_fma(packed, 148 * 8, 256, iters, sink.data_ptr(), stream), 'probe'), 5, 2)
+            ms = timed(lambda s: _cabi.check(lib.bas_probe_fma(packed, 148 * 8, 256, iters, sink.data_ptr(), stream), 'probe'), 5, 2, collective=False)
             fma[name] = 148 * 8 * 256 * iters * 32 / (ms * 1e-3) / 1e12
         fma_peak = max(fma.values())
         useful_fma = 2.0 * k * n_in                       # 2 ears x K taps per input sample

@@ -64,6 +64,8 @@ def render_mix_by_source(signals, chunksize, subchunksize, elev_azim_functions, 
     else:
         local = None
     local = _as_tensor(torch, local)
+    if local is not None:
+        local = local.contiguous()                  # the renderer returns a view of a padded buffer; NCCL wants dense
     # ranks without sources contribute zeros of the right shape
     shape = torch.tensor([0, 0] if local is None else list(local.shape), dtype=torch.int64,
                          device=local.device if local is not None else _collective_device(torch, dist, group))
@@ -106,10 +108,13 @@ def render_by_time(in_signal, chunksize, subchunksize, elev_azim_function, bank,
                      return_device=True, time_range=(p0 - n0, min(p1, n1 + k - 1) - n0))
         seg = _as_tensor(torch, seg)[0]
     dev = seg.device if seg is not None else _collective_device(torch, dist, group)
-    peak = torch.zeros(1, dtype=torch.float32, device=dev) if seg is None or seg.numel() == 0 else seg.abs().max().reshape(1)
+    peak = torch.zeros(1, dtype=torch.float32, device=dev)
+    if seg is not None and seg.numel():
+        seg = seg.contiguous()
+        _peak_into(torch, seg, peak)
     dist.all_reduce(peak, op=dist.ReduceOp.MAX, group=group)            # global apply_hrtf.py:462
-    if seg is not None and float(peak) > 1:
-        seg = seg / peak                                                # :464
+    if seg is not None and seg.numel():
+        _divide_by_peak(torch, seg, peak)                               # :463-464, only when the peak exceeds 1
     if not gather:
         return seg, (p0, p1)
     full = torch.zeros((2, n_out), dtype=torch.float32, device=dev)
@@ -118,6 +123,24 @@ def render_by_time(in_signal, chunksize, subchunksize, elev_azim_function, bank,
     dist.all_reduce(full, op=dist.ReduceOp.SUM, group=group)            # disjoint ranges: a gather
     out = full.cpu().numpy() if full.is_cuda else full.numpy()
     return out.T
+
+
+def _peak_into(torch, seg, peak):
+    """max |seg| into the one-element tensor `peak`: bas_peak on the device; torch only for the CPU
+    tensors a test's injected renderer returns."""
+    if seg.is_cuda:
+        from ._cabi import check, lib
+        check(lib.bas_peak(seg.data_ptr(), seg.numel(), peak.data_ptr(), torch.cuda.current_stream().cuda_stream), 'bas_peak')
+    else:
+        peak.copy_(seg.abs().max().reshape(1))
+
+
+def _divide_by_peak(torch, seg, peak):
+    if seg.is_cuda:
+        from ._cabi import check, lib
+        check(lib.bas_normalise(seg.data_ptr(), seg.numel(), peak.data_ptr(), torch.cuda.current_stream().cuda_stream), 'bas_normalise')
+    elif float(peak) > 1:
+        seg /= peak
 
 
 def _shift_trajectory(fn, offset: int):

@@ -1,0 +1,51 @@
+"""Multi-GPU check of the two shardings (run under torchrun, backend nccl):
+    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29533 tools/dist_check.py
+by source: every rank renders and mixes its own sources, NCCL SUM -> compare with one GPU mixing all of them;
+by time:   one long source cut across the ranks with an input halo, NCCL MAX of the peak -> compare with
+           make_signal_move_2d on one GPU."""
+import os, sys, json
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+import torch.distributed as dist
+import binaural_audio_synthesis_b200 as bas
+import bench
+
+rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
+torch.cuda.set_device(local)
+dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+bas.apply_hrtf.PROGRESS = False
+bank = bench.make_bank(bas)
+rel = lambda a, b: float(np.linalg.norm(a.astype(np.float64) - b) / np.linalg.norm(b))
+out = {}
+
+# ---- by source (configs 3, 5) ----
+n_src, n = 12, 5 * 44100
+sig = np.stack([bench.pink_noise(n, 100 + s) for s in range(n_src)])
+sig[3] *= 60.0                                     # one source that peaks above 1 and is normalised on its own
+trajs = [bench.lissajous(s) for s in range(n_src)]
+mine = bas.distributed.shard_sources(n_src, rank, world)
+mix = bas.distributed.render_mix_by_source(sig[mine], 512, 32, [trajs[s] for s in mine], bank)
+torch.cuda.synchronize()
+if rank == 0:
+    ref = bas.render_sources(sig, 512, 32, trajs, bank, mix=True)
+    out['by_source_rel_l2_vs_one_gpu'] = rel(mix.cpu().numpy(), ref.astype(np.float64))
+    out['by_source_shape'] = list(mix.shape)
+
+# ---- by time (config 4) ----
+x = 30.0 * bench.pink_noise(20 * 44100 + 123, 7)   # peaks above 1: exercises the global normalisation
+traj = bench.lissajous(3)
+full = bas.distributed.render_by_time(x, 512, 32, traj, bank, gather=True)
+if rank == 0:
+    ref = bas.make_signal_move_2d(x, 512, 32, traj, bank)
+    out['by_time_rel_l2_vs_one_gpu'] = rel(full, ref.astype(np.float64))
+    out['by_time_peak'] = float(np.abs(full).max())
+    out['by_time_shape'] = list(full.shape)
+    ok = out['by_source_rel_l2_vs_one_gpu'] < 1e-6 and out['by_time_rel_l2_vs_one_gpu'] < 1e-6 and abs(out['by_time_peak'] - 1) < 1e-6
+    out['world'] = world
+    out['ok'] = bool(ok)
+    print(json.dumps(out))
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if (rank != 0 or out['ok']) else 1)
