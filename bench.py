@@ -215,42 +215,57 @@ def run_ours(args, rank, local_rank, world):
             filt=torch.empty((n_pts, pitch, 2), dtype=torch.float32, device=dev),
             out=torch.empty((2, (n_out + 4) // 4 * 4), dtype=torch.float32, device=dev), peak=torch.zeros(1, dtype=torch.float32, device=dev)))
     out_stride = (n_out + 4) // 4 * 4
-    workspace = _cabi.render_workspace(torch, dev)
+    # sources in flight: consecutive steps (independent sources) alternate over this many streams, the
+    # way a server keeps several make_signal_move_2d calls going on one GPU.  plan_build (latency
+    # bound), ir_synth (L2 bound) and render (FP32 pipe bound) of neighbouring steps then overlap, and
+    # the next step's CTAs fill the SMs the last wave of a render leaves idle.
+    n_flight = max(1, args.in_flight)
+    streams = [torch.cuda.current_stream()] + [torch.cuda.Stream() for _ in range(n_flight - 1)]
+    workspaces = [torch.empty(int(lib.bas_render_workspace_bytes()), dtype=torch.uint8, device=dev) for _ in streams]
 
-    def step_render(s):
+    def step_render(s, lane=0):
+        st = streams[lane].cuda_stream
         _cabi.check(lib.bas_render(s['x'].data_ptr(), n_in, n_in, 1, n_in, CHUNK, SUB, k, s['filt'].data_ptr(), None,
                                    0, n_out, s['out'].data_ptr(), out_stride, 0, s['peak'].data_ptr(), args.variant,
-                                   workspace.data_ptr(), workspace.numel(), stream), 'bas_render')
+                                   workspaces[lane].data_ptr(), workspaces[lane].numel(), st), 'bas_render')
 
-    def step(s):
+    def step(s, lane=0):
+        st = streams[lane].cuda_stream
         _cabi.check(lib.bas_plan_build(bdev.diffs[0].data_ptr(), bdev.diffs[1].data_ptr(), UPS, k * UPS, s['elev'].data_ptr(),
                                        s['azim'].data_ptr(), None, _cabi.AZ_F64, n_pts, s['terms'].data_ptr(), None,
-                                       s['status'].data_ptr(), stream), 'bas_plan_build')
+                                       s['status'].data_ptr(), st), 'bas_plan_build')
         _cabi.check(lib.bas_ir_synth(bdev.bank_pp.data_ptr(), UPS, k, s['terms'].data_ptr(), n_pts, _cabi.IR_ROWS,
-                                     s['filt'].data_ptr(), k, stream), 'bas_ir_synth')
-        s['peak'].zero_()
-        step_render(s)
-        _cabi.check(lib.bas_normalise(s['out'].data_ptr(), 2 * out_stride, s['peak'].data_ptr(), stream), 'bas_normalise')
-    launches_per_step = 5        # plan, ir_synth, peak memset, render, normalise
+                                     s['filt'].data_ptr(), k, st), 'bas_ir_synth')
+        _cabi.check(lib.bas_memset(s['peak'].data_ptr(), 0, 4, st), 'bas_memset')
+        step_render(s, lane)
+        _cabi.check(lib.bas_normalise(s['out'].data_ptr(), 2 * out_stride, s['peak'].data_ptr(), st), 'bas_normalise')
+    launches_per_step = 7        # plan (2 status memsets + kernel), ir_synth, peak memset, render, normalise
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, collective=True):
+    def timed(fn, steps, warmup, collective=True, lanes=1):
         """ms per step of fn over `steps` steps after `warmup`: CUDA events on the launching stream,
-        bracketed by a barrier + synchronize, max over ranks.  collective=False: this rank only (the
-        per-kernel timings rank 0 takes for the roofline)."""
+        bracketed by a barrier + synchronize, max over ranks.  lanes > 1: step i runs on stream
+        i % lanes; the closing event is recorded after every stream has joined the first.
+        collective=False: this rank only (the per-kernel timings rank 0 takes for the roofline)."""
         sync = barrier if collective else torch.cuda.synchronize
         for i in range(warmup):
-            fn(sets[i % n_sets])
+            fn(sets[i % n_sets], i % lanes) if lanes > 1 else fn(sets[i % n_sets])
         sync()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        e0.record(streams[0])
+        for lane in range(1, lanes):
+            streams[lane].wait_event(e0)
         for i in range(steps):
-            fn(sets[(warmup + i) % n_sets])
-        e1.record()
+            fn(sets[(warmup + i) % n_sets], i % lanes) if lanes > 1 else fn(sets[(warmup + i) % n_sets])
+        for lane in range(1, lanes):
+            ev = torch.cuda.Event()
+            ev.record(streams[lane])
+            streams[0].wait_event(ev)
+        e1.record(streams[0])
         sync()
         ms = e0.elapsed_time(e1)
         if collective and dist is not None:
@@ -261,14 +276,15 @@ def run_ours(args, rank, local_rank, world):
 
     warmup = max(args.warmup, 3)
     with ClockSampler(local_rank) as clocks:
-        ms_step = timed(step, args.steps, warmup)
+        ms_step = timed(step, args.steps, warmup, lanes=n_flight)
+        ms_serial = timed(step, args.steps, warmup) if n_flight > 1 else ms_step
         # keep the sampler running over a longer stretch of the same work if the timed region was
         # too short for NVML to see it (clock evidence only; not part of any reported time)
         if len(clocks.samples) < 20:
             t_end = time.time() + 0.5
             while time.time() < t_end:
                 for i in range(20):
-                    step(sets[i % n_sets])
+                    step(sets[i % n_sets], i % n_flight)
                 torch.cuda.synchronize()
     assert int(sets[0]['status'].cpu()[0]) == 0
     value = world * n_out / (ms_step * 1e-3)
@@ -277,7 +293,10 @@ def run_ours(args, rank, local_rank, world):
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': warmup,
         'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic',
-        'config': {'workload': workload_name(), 'sources_per_gpu': 1, 'parallelism': 'source-sharded x%d, no data-path collective' % world,
+        'config': {'workload': workload_name(), 'sources_per_gpu': 1, 'sources_in_flight': n_flight,
+                   'in_flight_note': 'consecutive steps (independent sources) alternate over %d CUDA streams; one source at a time: '
+                                     '%.4f ms per step' % (n_flight, ms_serial),
+                   'parallelism': 'source-sharded x%d, no data-path collective' % world,
                    'l2_policy': 'steps rotate over %d buffer sets (%.0f MB > 126 MB L2)' % (n_sets, n_sets * set_bytes / 1e6),
                    'kernels_per_step': 'plan_build, ir_synth, render, normalise'},
         'clocks': clocks.summary(), 'gpu_launches': launches_per_step * args.steps,
@@ -300,6 +319,15 @@ def run_ours(args, rank, local_rank, world):
         else:
             hbm_peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
         achieved = algo_bytes / (ms_render * 1e-3) / 1e9
+        # DRAM bytes of one render launch from the committed ncu --set full capture of this command
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            for name, kv in tj['kernels'].items():
+                if name.startswith('bas_render_tiled_kernel'):
+                    traffic = kv['dram_bytes_read'] + kv['dram_bytes_write']
+                    traffic_src = 'profiles/r1_traffic.json (%s): %s; the 21 MB of output were still in the 126 MB L2 when the kernel ended' % (tj['source'], name)
         # FP32 pipe: measured FMA peak on this GPU, same session
         sink = torch.empty(148 * 8 * 256, dtype=torch.float32, device=dev)
         fma = {}
@@ -311,7 +339,7 @@ def run_ours(args, rank, local_rank, world):
         useful_fma = 2.0 * k * n_in                       # 2 ears x K taps per input sample
         line['roofline'] = {
             'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
-            'traffic': None, 'kernel': 'bas_render_tiled_kernel', 'ms_per_launch': ms_render, 'peak_source': peak_src,
+            'traffic': traffic, 'traffic_source': traffic_src, 'kernel': 'bas_render_tiled_kernel', 'ms_per_launch': ms_render, 'peak_source': peak_src,
             'algorithmic_bytes_per_launch': algo_bytes,
             'fp32_pipe': {'achieved_tfma_s': useful_fma / (ms_render * 1e-3) / 1e12, 'peak_tfma_s': fma_peak,
                           'frac': useful_fma / (ms_render * 1e-3) / 1e12 / fma_peak, 'probe': fma,
@@ -390,6 +418,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--variant', type=lambda v: int(v, 0), default=0, help='bas_render variant (tuning)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--in-flight', type=int, default=4, help='independent sources (steps) in flight per GPU, one CUDA stream each')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))

@@ -19,3 +19,9 @@ extern "C" int bas_copy_2d(void* dst, long long dst_pitch_bytes, const void* src
                                (size_t)rows, kind, (cudaStream_t)stream));
     return 0;
 }
+
+extern "C" int bas_memset(void* dev, int value, long long bytes, void* stream) {
+    BAS_CHECK_ARG(dev && bytes >= 0, "bad pointer or size");
+    if (bytes) BAS_CUDA(cudaMemsetAsync(dev, value, (size_t)bytes, (cudaStream_t)stream));
+    return 0;
+}

@@ -217,6 +217,9 @@ int bas_pipeline_phase(const bas_pipeline_job* job, int phase, int n_phases, lon
  * tracing on or off. */
 int bas_pipeline_trace(int enable, char* buf, size_t len);
 
+/* Asynchronous byte fill of device memory on `stream` (zeroing peaks before bas_render). */
+int bas_memset(void* dev, int value, long long bytes, void* stream);
+
 /* FP32 pipe probe used by bench.py to state the measured FMA peak beside the HBM roofline:
  * every thread runs `iters` rounds of 16 independent dependent-chain FMAs.
  * packed=0: fma.rn.f32 (32 FMA per thread per round) ; packed=1: fma.rn.f32x2 (same FMA count).
