@@ -5,10 +5,19 @@
 
 namespace {
 
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// mhz (optional): SM clock the kernel actually ran at, from clock64 against the nanosecond timer
 template <bool PACKED>
 __global__ void __launch_bounds__(256)
-bas_probe_fma_kernel(int iters, float* __restrict__ sink) {
+bas_probe_fma_kernel(int iters, float* __restrict__ sink, float* __restrict__ mhz = nullptr) {
     const float seed = (float)(threadIdx.x & 7) * 1e-3f;
+    long long c0 = 0; unsigned long long t0 = 0;
+    if (mhz && blockIdx.x == 0 && threadIdx.x == 0) { t0 = global_ns(); c0 = clock64(); }
     if (PACKED) {
         unsigned long long acc[16], a, b;
         asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(0.999f + seed), "f"(0.998f));
@@ -27,6 +36,7 @@ bas_probe_fma_kernel(int iters, float* __restrict__ sink) {
             s += lo + hi;
         }
         sink[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+        if (mhz && blockIdx.x == 0 && threadIdx.x == 0) { const long long c1 = clock64(); const unsigned long long t1 = global_ns(); *mhz = 1e3f * (float)(c1 - c0) / (float)(t1 - t0); }
     } else {
         float acc[32];
         const float a = 0.999f + seed, b = 1e-3f;
@@ -40,6 +50,7 @@ bas_probe_fma_kernel(int iters, float* __restrict__ sink) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) s += acc[i];
         sink[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+        if (mhz && blockIdx.x == 0 && threadIdx.x == 0) { const long long c1 = clock64(); const unsigned long long t1 = global_ns(); *mhz = 1e3f * (float)(c1 - c0) / (float)(t1 - t0); }
     }
 }
 
@@ -169,6 +180,16 @@ extern "C" int bas_probe_fma(int packed, int blocks, int threads, int iters, flo
     }
     if (packed) bas_probe_fma_kernel<true><<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, sink_dev);
     else bas_probe_fma_kernel<false><<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, sink_dev);
+    BAS_LAUNCH_CHECK();
+    return 0;
+}
+
+// The same FMA streams as bas_probe_fma (packed = 0 / 1), also reporting the SM clock they ran at.
+extern "C" int bas_probe_clock(int packed, int blocks, int threads, int iters, float* sink_dev, float* mhz_dev, void* stream) {
+    BAS_CHECK_ARG(sink_dev && mhz_dev, "null pointer");
+    BAS_CHECK_ARG((packed == 0 || packed == 1) && blocks >= 1 && threads >= 32 && threads <= 256 && threads % 32 == 0 && iters >= 1, "launch shape");
+    if (packed) bas_probe_fma_kernel<true><<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, sink_dev, mhz_dev);
+    else bas_probe_fma_kernel<false><<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, sink_dev, mhz_dev);
     BAS_LAUNCH_CHECK();
     return 0;
 }

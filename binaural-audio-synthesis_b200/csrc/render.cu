@@ -37,6 +37,9 @@
 //   epilogue Direct 16-byte global stores from registers, peak by warp reduction + one atomicMax.
 #include "render_tiled.cuh"
 
+#include <atomic>
+#include <chrono>
+
 using namespace bas_render_detail;
 
 namespace {
@@ -210,9 +213,22 @@ extern "C" int bas_render(const float* x_dev, long long x_stride, long long n_va
     return 0;
 }
 
+namespace bas_render_detail {
+unsigned long long next_epoch() {
+    static std::atomic<unsigned long long> counter{0};
+    static const unsigned long long salt = [] {
+        const auto t = std::chrono::high_resolution_clock::now().time_since_epoch().count();
+        unsigned long long z = (unsigned long long)t + 0x9E3779B97F4A7C15ull * (unsigned long long)(uintptr_t)&counter;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return (z ^ (z >> 31)) | 1ull;
+    }();
+    return (salt << 24) ^ (++counter);
+}
+}  // namespace bas_render_detail
+
 extern "C" long long bas_render_workspace_bytes(void) {
-    // resident warps (at most 16 per SM) x 2 slots x (1024 outputs x 2 ears) floats, whatever the tile shape
-    return (long long)device_sm_count() * 16 * 2 * (2LL * kWarpTile) * 4;
+    // resident stripes (at most 16 warps per SM): a flag and 1024 {L,R} partial sums each, whatever the shape
+    return (long long)ws_bytes((long long)device_sm_count() * 16, 1);
 }
 
 extern "C" int bas_peak(const float* v_dev, long long n, float* peak_dev, void* stream) {

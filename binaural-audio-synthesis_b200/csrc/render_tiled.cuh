@@ -182,11 +182,15 @@ __device__ __forceinline__ void block_diag(u64 (&acc)[kBlk], const float2* __res
 // tile:   one source per tile (MIX = false): group = (source, tile), slice = tap block d, gs = D
 //         mixing                (MIX = true): group = tile,           slice = source,      gs = n_src
 // CTA c owns the contiguous slice span [c*total/G, (c+1)*total/G).  A span boundary that falls
-// inside a group splits that group between exactly two CTAs (spans are longer than a group); both
-// write their partial tile to the workspace and bas_render_fixup_kernel adds the two in a fixed order,
-// so results stay deterministic while every scheduler gets the same number of 32x32 blocks.  Without
-// a workspace spans are rounded to group boundaries.
-struct SpanInfo { long long total, n_groups; int gs; int split; };
+// inside a group splits that group between exactly two CTAs (spans are longer than a group).  The
+// later CTA runs its share FIRST in its span, writes the partial stripe to the workspace and raises a
+// flag (st.release.gpu); the earlier CTA reaches the group LAST in its span, waits for the flag
+// (ld.acquire.gpu), adds the partial to its own sums - earlier part + later part, a fixed order - and
+// finishes the tile.  CTA c only ever waits for CTA c + 1, and for work c + 1 does before anything
+// else, so the wait cannot deadlock even when not all CTAs are resident at once.  Every scheduler
+// gets the same number of 32x32 blocks and results stay deterministic.  Without a workspace spans
+// are rounded to group boundaries.
+struct SpanInfo { long long total, n_groups; int gs; int split; unsigned long long epoch; };
 
 __host__ __device__ inline long long span_begin(const SpanInfo& sp, long long c, long long G) {
     if (sp.split) return (long long)(((unsigned long long)c * (unsigned long long)sp.total) / (unsigned long long)G);
@@ -200,6 +204,18 @@ struct Item {
     bool partial;           // this CTA holds only part of the group -> workspace
     int slot;               // workspace slot: 0 = group began in the previous CTA, 1 = continues in the next
 };
+
+__device__ __forceinline__ void flag_release(unsigned long long* flag, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(flag), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long flag_acquire(const unsigned long long* flag) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+    return v;
+}
+// workspace: one flag and one stripe of {L,R} partial sums per (CTA, stripe)
+__host__ __device__ inline size_t ws_flag_bytes(long long grid, int TS) { return ((size_t)grid * TS * 8 + 255) / 256 * 256; }
+__host__ __device__ inline size_t ws_bytes(long long grid, int TS) { return ws_flag_bytes(grid, TS) + (size_t)grid * TS * kWarpTile * 8; }
 
 __device__ __forceinline__ void cta_barrier(int threads) {
     asm volatile("bar.sync 1, %0;" ::"r"(threads) : "memory");
@@ -436,7 +452,26 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
         // ---- peak, gain, mix, store ----------------------------------------------------------------
         const long long pb = P0 + (long long)blk * kBlk;        // first output of this lane
         const float gain = prm.gains ? prm.gains[it.src] : 1.f;
-        if (prm.peaks && (MIX || !it.partial)) {                // split tiles get their peak in the fix-up
+        // a tile split between two CTAs: the later CTA (slot 0) publishes its partial sums, the earlier
+        // one (slot 1) adds them to its own and finishes the tile
+        const bool publish = it.partial && it.slot == 0, adopt = it.partial && it.slot == 1;
+        unsigned long long* ws_flags = reinterpret_cast<unsigned long long*>(workspace);
+        u64* ws_sums = reinterpret_cast<u64*>(reinterpret_cast<unsigned char*>(workspace) + ws_flag_bytes(gridDim.x, TS));
+        if (!MIX && adopt && it.group_end && warp_live) {
+            const long long slot = (long long)(blockIdx.x + 1) * TS + stripe;
+            if (lane == 0) {
+                unsigned spins = 0;
+                while (flag_acquire(ws_flags + slot) != sp.epoch) {
+                    __nanosleep(64);
+                    if (++spins > (1u << 24)) __trap();             // the neighbour never published: fail loudly
+                }
+            }
+            __syncwarp();
+            const u64* srcp = ws_sums + slot * kWarpTile + lane;
+#pragma unroll
+            for (int r = 0; r < kBlk; ++r) acc[r] = add2(acc[r], __ldcg(srcp + r * 32));
+        }
+        if (prm.peaks && (MIX || !publish)) {
             float pk = 0.f;
 #pragma unroll
             for (int r = 0; r < kBlk; ++r) {
@@ -457,18 +492,32 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
                 acc[r] = fma2(g2, acc[r], prev);
                 if (!it.group_end) { mixbuf[r * 32 + lane] = acc[r]; acc[r] = 0ull; }
             }
+            if (adopt && it.group_end && warp_live) {           // earlier sources (here) + later sources (next CTA)
+                const long long slot = (long long)(blockIdx.x + 1) * TS + stripe;
+                if (lane == 0) {
+                    unsigned spins = 0;
+                    while (flag_acquire(ws_flags + slot) != sp.epoch) {
+                        __nanosleep(64);
+                        if (++spins > (1u << 24)) __trap();
+                    }
+                }
+                __syncwarp();
+                const u64* srcp = ws_sums + slot * kWarpTile + lane;
+#pragma unroll
+                for (int r = 0; r < kBlk; ++r) acc[r] = add2(acc[r], __ldcg(srcp + r * 32));
+            }
         }
         if (it.group_end) {
-            if (it.partial) {
-                // partial tile -> workspace[cta][slot][ear][T], no gain (one source per tile) / mixed
-                float* w = workspace + ((long long)blockIdx.x * 2 + it.slot) * (2 * T) + blk * kBlk;
+            if (publish) {
+                // partial stripe -> workspace[cta][stripe][r][lane] {L,R}, no gain (one source per tile) / mixed
+                if (warp_live) {
+                    const long long slot = (long long)blockIdx.x * TS + stripe;
+                    u64* dstp = ws_sums + slot * kWarpTile + lane;
 #pragma unroll
-                for (int r4 = 0; r4 < kBlk; r4 += 4) {
-                    float l[4], rr[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) unpack2(acc[r4 + i], l[i], rr[i]);
-                    *reinterpret_cast<float4*>(w + r4) = make_float4(l[0], l[1], l[2], l[3]);
-                    *reinterpret_cast<float4*>(w + T + r4) = make_float4(rr[0], rr[1], rr[2], rr[3]);
+                    for (int r = 0; r < kBlk; ++r) __stcg(dstp + r * 32, acc[r]);
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) flag_release(ws_flags + slot, sp.epoch);
                 }
             } else {
                 float* o = prm.out + (MIX ? 0 : (long long)it.src * 2 * prm.out_stride);
@@ -500,41 +549,9 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
     }
 }
 
-// Adds the two partial tiles of every group a span boundary split (fixed order: the earlier CTA's
-// part first), applies the gain, takes the peak and stores.  grid = (boundaries, 2 ears, T / 1024).
-static __global__ void __launch_bounds__(256)
-bas_render_fixup_kernel(RenderParams prm, SpanInfo sp, const float* __restrict__ workspace, long long G, int TS) {
-    const long long c = blockIdx.x + 1;                           // boundary between CTA c-1 and CTA c
-    const int ear = blockIdx.y;
-    const long long ic = span_begin(sp, c, G);
-    if (ic % sp.gs == 0 || ic >= sp.total) return;                // boundary on a group edge: nothing was split
-    const long long grp = ic / sp.gs;
-    const int T = TS * kWarpTile;
-    const int src = prm.mix ? 0 : (int)(grp / prm.tiles);
-    const long long tile = prm.mix ? grp : grp - (long long)src * prm.tiles;
-    const long long p_base = prm.p_begin / kBlk * kBlk;
-    const int i = blockIdx.z * kWarpTile + threadIdx.x * 4;       // 256 threads x 4 outputs
-    const long long p = p_base + tile * T + i;
-    const float4 a = *reinterpret_cast<const float4*>(workspace + ((c - 1) * 2 + 1) * (2LL * T) + (long long)ear * T + i);
-    const float4 b = *reinterpret_cast<const float4*>(workspace + (c * 2 + 0) * (2LL * T) + (long long)ear * T + i);
-    const float gain = (!prm.mix && prm.gains) ? prm.gains[src] : 1.f;
-    float* o = prm.out + (prm.mix ? 0 : (long long)src * 2 * prm.out_stride) + (long long)ear * prm.out_stride;
-    const float v[4] = {a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w};
-    float pk = 0.f;
-    const bool vec_ok = (prm.p_begin & 3) == 0 && (prm.out_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(prm.out) & 15) == 0;
-    if (vec_ok && p >= prm.p_begin && p + 4 <= prm.p_end) {
-        pk = fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3])));
-        *reinterpret_cast<float4*>(o + (p - prm.p_begin)) = make_float4(gain * v[0], gain * v[1], gain * v[2], gain * v[3]);
-    } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-            if (p + e >= prm.p_begin && p + e < prm.p_end) { pk = fmaxf(pk, fabsf(v[e])); o[p + e - prm.p_begin] = gain * v[e]; }
-    }
-    if (prm.peaks && !prm.mix) {
-        pk = warp_max(pk);
-        if ((threadIdx.x & 31) == 0 && pk > 0.f) atomic_max_nonneg(prm.peaks + src, pk);
-    }
-}
+// Launch stamp the hand-off flags of a split launch are compared with: unique per launch of this
+// process (random salt in the high bits), so stale flags in the caller's workspace never match.
+unsigned long long next_epoch();
 
 inline int device_sm_count() {
     static thread_local int sm_count = 0;
@@ -589,17 +606,12 @@ int launch_tiled(RenderParams prm, int parts, bool want_split, float* workspace,
     if (grid > sp.n_groups) grid = sp.n_groups;
     // split groups between CTAs only when every span is longer than a group (then a group has at
     // most two contributors) and the caller gave a workspace
-    const long long need = grid * 2 * (2LL * TS * kWarpTile) * 4;
+    const long long need = (long long)ws_bytes(grid, TS);
     sp.split = (want_split && workspace && workspace_bytes >= need && grid > 1 && sp.total / grid >= sp.gs + 1) ? 1 : 0;
+    sp.epoch = sp.split ? next_epoch() : 0ull;
     kern<<<(unsigned)grid, TW * 32, smem, st>>>(prm, sp, workspace);
     e = cudaGetLastError();
     if (e != cudaSuccess) { bas_set_error("bas_render: tiled launch failed: %s", cudaGetErrorString(e)); return (int)e; }
-    if (sp.split) {
-        dim3 fgrid((unsigned)(grid - 1), 2, (unsigned)TS);
-        bas_render_fixup_kernel<<<fgrid, 256, 0, st>>>(prm, sp, workspace, grid, TS);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) { bas_set_error("bas_render: fix-up launch failed: %s", cudaGetErrorString(e)); return (int)e; }
-    }
     return 0;
 }
 

@@ -141,9 +141,11 @@ int bas_render(const float* x_dev, long long x_stride, long long n_valid, int n_
                long long p_begin, long long p_count, float* out_dev, long long out_stride, int mix,
                float* peaks_dev, int variant, void* workspace_dev, long long workspace_bytes, void* stream);
 
-/* Scratch the tiled renderer may use to balance work across SMs (a tile split between two CTAs is
- * summed there in a fixed order, so results stay deterministic).  workspace_dev may be NULL: tiles
- * are then never split.  Contents need no initialisation and carry nothing between calls. */
+/* Scratch the tiled renderer may use to balance work across SMs: a tile split between two CTAs is
+ * handed from one to the other through it (partial sums + a release/acquire flag per stripe, added
+ * in a fixed order, so results stay deterministic).  workspace_dev may be NULL: tiles are then never
+ * split.  Contents need no initialisation and carry nothing between calls; concurrent bas_render
+ * calls (different streams) need a workspace each. */
 long long bas_render_workspace_bytes(void);
 
 /* apply_hrtf.py:462-464: divide n floats by *peak_dev when it exceeds 1 (no-op otherwise). */
@@ -226,6 +228,10 @@ int bas_memset(void* dev, int value, long long bytes, void* stream);
  * sink_dev receives one float per thread so the work cannot be elided.  FMA count of the launch =
  * blocks * threads * iters * 32. */
 int bas_probe_fma(int packed, int blocks, int threads, int iters, float* sink_dev, void* stream);
+
+/* bas_probe_fma (packed = 0 / 1) that also reports the SM clock (MHz) the stream ran at, measured on the
+ * device (clock64 against the nanosecond global timer): what the FMA peak has to be read against. */
+int bas_probe_clock(int packed, int blocks, int threads, int iters, float* sink_dev, float* mhz_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -48,7 +48,7 @@ def main():
     workspace = _cabi.render_workspace(torch, dev)
     for (tw, ns, ctas) in ((0, 0, 0),) + tuple(_cabi.TILED_SHAPES):
         for parts in (0, 1, 2, 4):
-            for split in ((False, True) if mix else (False,)):
+            for split in (False, True):
                 if (tw == 0) != (parts == 0) or (tw and tw % parts):
                     continue
                 if only_tw and tw != only_tw:
