@@ -722,3 +722,53 @@ def make_signal_move_2d(in_signal, chunksize: int, subchunksize: int, elev_azim_
     if PROGRESS:
         print(' 100.0%      ')                                                      # :457
     return out[0].T                                                                 # (N_out, 2), planar memory like :459
+
+
+def make_signal_move(in_signal, chunksize: int, index_function, irs_and_delaydiffs):
+    """apply_hrtf.py:294-353, the legacy 1-D renderer (superseded by make_signal_move_2d per its own
+    docstring): index_function(t) gives a continuous index on the horizontal ring; every chunk is
+    convolved with ONE ring-interpolated filter (delay_compensated_interpolation_easy, no cross-fade)
+    and overlap-added.  Same kernels as the 2-D path: the scalar part of the ring interpolation per
+    chunk on the host (bas_plan_ring_host), bas_ir_synth for the filters, and bas_render with
+    subchunksize = chunksize, for which every blend weight alpha_q is zero."""
+    torch = _cabi.require_device()
+    assert len(in_signal.shape) == 1, 'only mono signals for now'                   # apply_hrtf.py:308
+    dev = _device_bank(irs_and_delaydiffs)
+    device = dev.device
+    k = int(0.5 + irs_and_delaydiffs.irs_left.shape[1] / irs_and_delaydiffs.upsampling)
+    n = in_signal.size
+    n_in = int(0.5 + np.ceil(n / chunksize) * chunksize)
+    n_out = n_in + k - 1
+    n_chunks = n_in // chunksize
+    terms = np.zeros((n_chunks + 1, 2, _cabi.MAX_TERMS), dtype=_cabi.TERM_DTYPE)
+    delays = np.zeros(2, dtype=np.float64)
+    for c in range(n_chunks):
+        ci = index_function(c * chunksize)                                          # :334
+        before, after = int(np.floor(ci)), int(np.ceil(ci))                         # :118-119
+        alpha = ci - before
+        if after == 97:
+            after = 73                                                              # :121-122
+        rc = lib.bas_plan_ring_host(dev.diffs_host[0].ctypes.data, dev.diffs_host[1].ctypes.data, dev.upsampling, dev.length,
+                                    _grid_row(before), _grid_row(after), float(alpha), float(1 - alpha),
+                                    terms[c].ctypes.data, delays.ctypes.data, None, None)
+        if rc < 0:
+            raise BasError(_cabi.last_error())
+        _raise_plan_error(rc, ' (chunk %d)' % c)
+    terms[n_chunks] = terms[n_chunks - 1]         # the boundary after the last chunk: present in the layout, weight 0
+    stream = _stream(torch)
+    terms_dev = torch.from_numpy(terms.view(np.uint8).reshape(-1)).to(device)
+    filt = torch.empty((n_chunks + 1, lib.bas_filter_row_pitch(k), 2), dtype=torch.float32, device=device)
+    _cabi.check(lib.bas_ir_synth(dev.bank_pp.data_ptr(), dev.upsampling, k, terms_dev.data_ptr(), n_chunks + 1, _cabi.IR_ROWS,
+                                 filt.data_ptr(), k, stream), 'bas_ir_synth')
+    x = torch.zeros(n_in, dtype=torch.float32, device=device)
+    x[:n] = torch.from_numpy(np.ascontiguousarray(in_signal, dtype=np.float32)).to(device)
+    stride = _round_up(n_out, 4)
+    out = torch.empty((2, stride), dtype=torch.float32, device=device)
+    peak = torch.zeros(1, dtype=torch.float32, device=device)
+    variant = _cabi.RENDER_AUTO if chunksize == 32 else _cabi.RENDER_GENERIC
+    _cabi.check(lib.bas_render(x.data_ptr(), n_in, n_in, 1, n_in, chunksize, chunksize, k, filt.data_ptr(), None, 0, n_out,
+                               out.data_ptr(), stride, 0, peak.data_ptr(), variant, None, 0, stream), 'bas_render')
+    _cabi.check(lib.bas_normalise(out.data_ptr(), 2 * stride, peak.data_ptr(), stream), 'bas_normalise')   # :349-351
+    if PROGRESS:
+        print(' 100.0%      ')                                                      # :346
+    return out[:, :n_out].cpu().numpy().T

@@ -258,6 +258,31 @@ def make_signal_move_2d(in_signal, chunksize: int, subchunksize: int, elev_azim_
     return finish(render_unnormalised(in_signal, chunksize, subchunksize, filters, k))
 
 
+def ring_interpolation_easy(bank, continuous_index):
+    """delay_compensated_interpolation_easy, apply_hrtf.py:114-125 (horizontal ring, 97 wraps to 73)."""
+    before = int(np.floor(continuous_index))
+    after = int(np.ceil(continuous_index))
+    alpha = continuous_index - before
+    if after == 97:
+        after = 73
+    return ring_interpolation(bank, before, after, alpha)[2]
+
+
+def make_signal_move(in_signal, chunksize: int, index_function, bank):
+    """The legacy 1-D renderer, apply_hrtf.py:294-353: one ring-interpolated filter per chunk (no
+    cross-fade), full convolution of every chunk, overlap-add, float32 cast and peak division."""
+    assert len(in_signal.shape) == 1, 'only mono signals for now'    # :308
+    k = int(0.5 + bank.irs_left.shape[1] / bank.upsampling)         # :309
+    n_in = int(0.5 + np.ceil(in_signal.size / chunksize) * chunksize)
+    x = np.pad(np.asarray(in_signal), (0, n_in - in_signal.size), mode='constant')
+    out = np.zeros((2, n_in + k - 1))
+    for i in range(0, n_in, chunksize):                              # :331
+        ir = ring_interpolation_easy(bank, index_function(i))       # :334
+        for ear in range(2):
+            out[ear, i:i + chunksize + k - 1] += np.convolve(x[i:i + chunksize], ir[ear])    # :337-343
+    return finish(out)                                               # :348-353
+
+
 # --------------------------------------------------------------------------------------
 # closed forms used by property tests (derived in SURVEY.md section 3.2 / 3.3)
 # --------------------------------------------------------------------------------------

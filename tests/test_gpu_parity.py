@@ -319,3 +319,46 @@ def test_host_pipeline_equals_device_path(bas, synth_bank, phases, seg_bytes, mo
     # and with the library's own choice of shapes: same result to rounding
     auto = bas.render_sources(xp, 512, 32, pre, synth_bank, normalise=False)
     assert rel_l2(auto, full) <= 1e-6
+
+
+def test_legacy_make_signal_move_vs_golden(bas, oracle, golden_bank):
+    """The legacy 1-D renderer (apply_hrtf.py:294-353) and delay_compensated_interpolation_easy
+    (:114-125) against outputs of the unmodified reference (tests/golden/reference_legacy.npz)."""
+    from .test_oracle_golden import _legacy, legacy_index_function
+    bas.apply_hrtf.PROGRESS = False
+    g = _legacy()
+    for v, want in zip(g['easy_in'], g['easy_out']):
+        close(bas.delay_compensated_interpolation_easy(golden_bank, float(v)), want)
+    for i in range(5):
+        name, chunk = g['legacy%d_meta' % i]
+        got = bas.make_signal_move(g['legacy%d_x' % i], int(chunk), legacy_index_function(name), golden_bank)
+        want = g['legacy%d_y' % i]
+        assert got.dtype == np.float32
+        close(got, want)
+    assert abs(np.abs(g['legacy4_y']).max() - 1.0) < 1e-6          # that case exercises the peak division
+
+
+def test_cli_writes_the_reference_file_name(bas, oracle, golden_bank, tmp_path, capsys):
+    """`python -m binaural_audio_synthesis_b200 in.wav` = the reference's main (apply_hrtf.py:559-649):
+    scale by the maximum, fold stereo to mono, render along `passing`, write in-c512-s32-l<K>.wav."""
+    from scipy.io import wavfile
+    from binaural_audio_synthesis_b200 import cli
+    fs = 8000
+    rng = np.random.default_rng(9)
+    stereo = (3000 * rng.standard_normal((6000, 2))).astype(np.int16)
+    wav = tmp_path / 'clip.wav'
+    wavfile.write(str(wav), fs, stereo)
+    mat = tmp_path / 'bank.mat'
+    bas.bank_synth.write_mat(str(mat), dict(upsampling=float(golden_bank.upsampling), diffs_left=golden_bank.diffs_left,
+                                            diffs_right=golden_bank.diffs_right, irs_left=golden_bank.irs_left,
+                                            irs_right=golden_bank.irs_right))
+    assert cli.main([str(wav), '--bank', str(mat), '--samples-to-keep', '32']) == 0
+    out_file = tmp_path / 'clip-c512-s32-l32.wav'
+    assert out_file.exists() and 'as fast as real time' in capsys.readouterr().out
+    fs_out, got = wavfile.read(str(out_file))
+    y = stereo.astype(np.float32) / stereo.max()
+    mono = 0.5 * y[:, 0] + 0.5 * y[:, 1]
+    want = oracle.make_signal_move_2d(mono, 512, 32, cli.trajectories(fs)['passing'], golden_bank)
+    assert fs_out == fs and got.dtype == np.float32
+    close(got, want)
+    assert cli.main([]) == 1                                       # no input file: the reference exits 1 (:570-574)
