@@ -5,7 +5,7 @@ kernels behind the C ABI of include/bas_b200.h.  No CPU fallback.
 
 Import as `binaural_audio_synthesis_b200` (see the alias package of that name).
 """
-from . import _cabi, sphere, apply_hrtf, bank_synth, distributed          # noqa: F401
+from . import _cabi, sphere, apply_hrtf, bank_synth, bank_builder, distributed          # noqa: F401
 from ._cabi import BasError                                                # noqa: F401
 from .apply_hrtf import (                                                  # noqa: F401
     load_irs_and_delaydiffs,
@@ -27,6 +27,6 @@ __all__ = [
     'load_irs_and_delaydiffs', 'delay_compensated_interpolation_with_delaydiff',
     'delay_compensated_interpolation', 'delay_compensated_interpolation_easy', 'interpolate_2d',
     'interpolate_2d_deg', 'interpolate_2d_batch', 'make_signal_move_2d', 'make_signal_move', 'render_sources',
-    'render_geometry', 'evaluate_trajectory', 'plan_points_host', 'sphere', 'bank_synth', 'distributed',
+    'render_geometry', 'evaluate_trajectory', 'plan_points_host', 'sphere', 'bank_synth', 'bank_builder', 'distributed',
     'BasError',
 ]

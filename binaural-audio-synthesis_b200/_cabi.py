@@ -79,6 +79,8 @@ def _load():
         'bas_last_error': ([C.c_char_p, C.c_size_t], i),
         'bas_device_count': ([], i),
         'bas_bank_to_polyphase': ([vp, i, i, i, vp, vp], i),
+        'bas_bank_upsample': ([vp, i, i, i, vp, i, vp, vp], i),
+        'bas_bank_delay_diffs': ([vp, i, i, i, vp, i, vp, vp], i),
         'bas_plan_build': ([vp, vp, i, i, vp, vp, vp, i, ll, vp, vp, vp, vp], i),
         'bas_plan_build_host': ([vp, vp, i, i, vp, vp, vp, i, ll, vp, vp], i),
         'bas_ring_lookup_host': ([C.c_double, C.c_double, i, C.POINTER(i), dp, C.POINTER(i)], i),

@@ -69,6 +69,18 @@ int bas_device_count(void);
  * out_dev:   n_rows x U x K floats, polyphase order: out[row][n % U][n / U] = irs[row][n].  */
 int bas_bank_to_polyphase(const double* irs_dev, int n_rows, int L, int U, float* out_dev, void* stream);
 
+/* ---- bank builder: the offline preprocessing of upsample_irs.m (the input side of the path) ----
+ * hrir_dev: n_rows x n doubles, one ear's measured HRIRs (content_m, upsample_irs.m:25-26).
+ * h_dev:    the resampling FIR, n_taps = 2 Lh + 1 doubles (zero phase; designed on the host, see
+ *           bank_builder.py), applied as y[m] = sum_k h[Lh + m - k U] x[k].
+ * bas_bank_upsample    -> out_dev: n_rows x (n U) doubles = resample(row, U, 1)      (:42-43)
+ * bas_bank_delay_diffs -> diffs_dev: n_rows x n_rows doubles, delaydifference of every pair i < j
+ *                         (:59-77, parabolic peak :88-101), antisymmetrised (:31-32), zero diagonal. */
+int bas_bank_upsample(const double* hrir_dev, int n_rows, int n, int U, const double* h_dev, int n_taps,
+                      double* out_dev, void* stream);
+int bas_bank_delay_diffs(const double* hrir_dev, int n_rows, int n, int U, const double* h_dev, int n_taps,
+                         double* diffs_dev, void* stream);
+
 /* ---- plan: the scalar part of interpolate_2d, apply_hrtf.py:199-215, :244-252, :261-266,
  *      :272-273, :149-151 and sphere.azim_to_interpolation_params, sphere.py:78-121 -----------
  * diffs_*_dev: 187 x 187 doubles row-major.  elev/azim: n_points doubles (radians).
