@@ -128,11 +128,14 @@ _workspaces = {}
 
 
 def render_workspace(torch, device):
-    """Per-device scratch for bas_render's tile splitting (allocated once, ~19 MB)."""
-    ws = _workspaces.get(device.index)
+    """Scratch for bas_render's tile splitting (~19 MB), one per (device, host thread, current stream):
+    concurrent renders must not share it (include/bas_b200.h)."""
+    import threading
+    key = (device.index, threading.get_ident(), torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
     if ws is None:
         ws = torch.empty(int(lib.bas_render_workspace_bytes()), dtype=torch.uint8, device=device)
-        _workspaces[device.index] = ws
+        _workspaces[key] = ws
     return ws
 
 

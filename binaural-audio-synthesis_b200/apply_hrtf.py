@@ -337,17 +337,6 @@ PIPELINE_MAX_SEGMENTS = 64
 _SEGMENT_ALIGN = 8192            # output samples; a whole number of render tiles for every tile width
 
 _side_streams = {}
-TIMELINE = None                  # tools/e2e_timeline.py sets this to a list to collect (label, host time, event)
-
-
-def _mark(torch, label, stream=None):
-    if TIMELINE is not None:
-        import time
-        ev = None
-        if stream is not None:
-            ev = torch.cuda.Event(enable_timing=True)
-            ev.record(stream)
-        TIMELINE.append((label, time.perf_counter(), ev))
 
 
 def _streams(torch, device):
@@ -569,7 +558,6 @@ def render_sources(signals, chunksize: int, subchunksize: int, elev_azim_functio
     device = dev.device
     main = torch.cuda.current_stream()
     stream = main.cuda_stream
-    _mark(torch, 'start', main)
     if isinstance(signals, torch.Tensor):
         src = signals
     else:
@@ -610,11 +598,9 @@ def render_sources(signals, chunksize: int, subchunksize: int, elev_azim_functio
                                         up.cuda_stream), 'bas_copy_2d')
             uploaded = torch.cuda.Event()
             uploaded.record(up)
-            _mark(torch, 'upload', up)
 
     # ---- directions at the chunk boundaries -> HBM (one pinned staging buffer, one copy) ----------
     elev, azim, kinds = _directions(elev_azim_functions, n_src, n_in, chunksize)
-    _mark(torch, 'h:trajectory')
     if isinstance(elev, torch.Tensor) or isinstance(azim, torch.Tensor):
         elev_d = torch.as_tensor(elev, dtype=torch.float64).to(device).contiguous()
         azim_d = torch.as_tensor(azim, dtype=torch.float64).to(device).contiguous()
@@ -627,15 +613,12 @@ def render_sources(signals, chunksize: int, subchunksize: int, elev_azim_functio
         host[1] = np.asarray(azim, dtype=np.float64).reshape(-1)
         both = staged.to(device, non_blocking=True)
         elev_d, azim_d = both[0], both[1]
-        _mark(torch, 'h:staged')
     if elev_d.numel() != n_src * n_pts or azim_d.numel() != n_src * n_pts:
         raise ValueError('trajectories must give %d directions per source' % n_pts)
     # status (2 ints) and per-source peaks share one buffer: one memset, one copy back
     small_dev = torch.zeros(2 + n_src, dtype=torch.int32, device=device)
     status, peaks = small_dev[:2], small_dev[2:].view(torch.float32)
-    _mark(torch, 'h:zeros')
     filt, _, _ = _plan_and_synth(torch, dev, elev_d, azim_d, kinds, n_src * n_pts, _cabi.IR_ROWS, status=status)
-    _mark(torch, 'filters', main)
     if uploaded is not None:
         main.wait_event(uploaded)
 
@@ -669,9 +652,7 @@ def render_sources(signals, chunksize: int, subchunksize: int, elev_azim_functio
             ev = torch.cuda.Event()
             ev.record(main)
             down.wait_event(ev)
-            _mark(torch, 'render %d' % i, main)
             download(pa, pb, down)
-            _mark(torch, 'down %d' % i, down)
         fetch_small(down)
         down.synchronize()
         second_pass = normalise
