@@ -337,6 +337,7 @@ PIPELINE_MAX_SEGMENTS = 64
 _SEGMENT_ALIGN = 8192            # output samples; a whole number of render tiles for every tile width
 
 _side_streams = {}
+MIX_GROUP_SOURCES = 16           # mixing more sources than this: groups, planned / synthesised while the previous group renders
 
 
 def _streams(torch, device):
@@ -618,20 +619,60 @@ def render_sources(signals, chunksize: int, subchunksize: int, elev_azim_functio
     # status (2 ints) and per-source peaks share one buffer: one memset, one copy back
     small_dev = torch.zeros(2 + n_src, dtype=torch.int32, device=device)
     status, peaks = small_dev[:2], small_dev[2:].view(torch.float32)
-    filt, _, _ = _plan_and_synth(torch, dev, elev_d, azim_d, kinds, n_src * n_pts, _cabi.IR_ROWS, status=status)
-    if uploaded is not None:
-        main.wait_event(uploaded)
-
     stride = _round_up(max(count, 1), 4)
     n_rows = 1 if mix else n_src
     out = torch.empty((n_rows, 2, stride), dtype=torch.float32, device=device)
     workspace = _cabi.render_workspace(torch, device)
+    grouped = mix and return_device and n_src > MIX_GROUP_SOURCES and count > 0
+    if not grouped:
+        filt, _, _ = _plan_and_synth(torch, dev, elev_d, azim_d, kinds, n_src * n_pts, _cabi.IR_ROWS, status=status)
+        if uploaded is not None:
+            main.wait_event(uploaded)
 
-    def launch(gains, pa, pb):
-        _cabi.check(lib.bas_render(x.data_ptr(), n_in, n_in, n_src, n_in, chunksize, subchunksize, k,
-                                   filt.data_ptr(), gains.data_ptr() if gains is not None else None,
-                                   pa, pb - pa, out.data_ptr() + 4 * (pa - p0), stride, 1 if mix else 0, peaks.data_ptr(),
-                                   variant, workspace.data_ptr(), workspace.numel(), stream), 'bas_render')
+        def launch(gains, pa, pb):
+            _cabi.check(lib.bas_render(x.data_ptr(), n_in, n_in, n_src, n_in, chunksize, subchunksize, k,
+                                       filt.data_ptr(), gains.data_ptr() if gains is not None else None,
+                                       pa, pb - pa, out.data_ptr() + 4 * (pa - p0), stride, 1 if mix else 0, peaks.data_ptr(),
+                                       variant, workspace.data_ptr(), workspace.numel(), stream), 'bas_render')
+    else:
+        # Many sources mixed into one output: groups of sources are planned and synthesised (latency /
+        # L2 bound) on a side stream while the previous group renders (FP32-pipe bound) on the main one;
+        # every group after the first ADDS its mix to the output (BAS_MIX_ACCUMULATE), groups in order.
+        if uploaded is not None:
+            main.wait_event(uploaded)
+        elev_f, azim_f = elev_d.reshape(-1), azim_d.reshape(-1)
+        kinds_d = None if np.isscalar(kinds) else torch.as_tensor(np.ascontiguousarray(kinds, dtype=np.uint8).reshape(-1)).to(device)
+        g_pts = MIX_GROUP_SOURCES * n_pts
+        pitch = lib.bas_filter_row_pitch(k)
+        terms_buf = [torch.empty(g_pts * 2 * _cabi.MAX_TERMS * 8, dtype=torch.uint8, device=device) for _ in range(2)]
+        filt_buf = [torch.empty((g_pts, pitch, 2), dtype=torch.float32, device=device) for _ in range(2)]
+        groups = [(s0, min(n_src, s0 + MIX_GROUP_SOURCES)) for s0 in range(0, n_src, MIX_GROUP_SOURCES)]
+        status_all = torch.zeros((len(groups), 2), dtype=torch.int32, device=device)
+
+        def launch(gains, pa, pb):
+            up.wait_stream(main)                                 # buffers above were allocated on `main`
+            rendered = [None, None]
+            for gi, (s0, s1) in enumerate(groups):
+                b, m = gi & 1, (s1 - s0) * n_pts
+                if rendered[b] is not None:
+                    up.wait_event(rendered[b])                   # the render two groups back has left this buffer
+                _cabi.check(lib.bas_plan_build(dev.diffs[0].data_ptr(), dev.diffs[1].data_ptr(), dev.upsampling, dev.length,
+                                               elev_f.data_ptr() + 8 * s0 * n_pts, azim_f.data_ptr() + 8 * s0 * n_pts,
+                                               kinds_d.data_ptr() + s0 * n_pts if kinds_d is not None else None,
+                                               0 if kinds_d is not None else int(kinds), m, terms_buf[b].data_ptr(), None,
+                                               status_all[gi].data_ptr(), up.cuda_stream), 'bas_plan_build')
+                _cabi.check(lib.bas_ir_synth(dev.bank_pp.data_ptr(), dev.upsampling, k, terms_buf[b].data_ptr(), m, _cabi.IR_ROWS,
+                                             filt_buf[b].data_ptr(), k, up.cuda_stream), 'bas_ir_synth')
+                ready = torch.cuda.Event()
+                ready.record(up)
+                main.wait_event(ready)
+                _cabi.check(lib.bas_render(x.data_ptr() + 4 * s0 * n_in, n_in, n_in, s1 - s0, n_in, chunksize, subchunksize, k,
+                                           filt_buf[b].data_ptr(), gains.data_ptr() + 4 * s0 if gains is not None else None,
+                                           pa, pb - pa, out.data_ptr() + 4 * (pa - p0), stride, 1 if gi == 0 else _cabi.MIX_ACCUMULATE,
+                                           peaks.data_ptr() + 4 * s0, variant, workspace.data_ptr(), workspace.numel(), stream),
+                            'bas_render')
+                rendered[b] = torch.cuda.Event()
+                rendered[b].record(main)
 
     small = torch.empty(2 + n_src, dtype=torch.int32, pin_memory=True)
     host_out = None if return_device else torch.empty((n_rows, 2, count), dtype=torch.float32, pin_memory=True)
@@ -668,6 +709,11 @@ def render_sources(signals, chunksize: int, subchunksize: int, elev_azim_functio
 
     host = small.numpy()
     err, where = int(host[0]), int(host[1])
+    if grouped:                                  # one status pair per source group: first failing direction overall
+        per_group = status_all.cpu().numpy()
+        for gi in np.nonzero(per_group[:, 0])[0]:
+            err |= int(per_group[gi, 0])
+            where = min(where if where else 0x7f7f7f7f, int(per_group[gi, 1]) + int(gi) * MIX_GROUP_SOURCES * n_pts)
     if err:
         _raise_plan_error(err, ' (trajectory point %d of source %d)' % (where % n_pts, where // n_pts))
     peaks_host = host[2:].view(np.float32).copy()

@@ -88,6 +88,7 @@ bas_render_generic_kernel(RenderParams prm) {
         }
     }
     if (prm.mix && live) {
+        if (prm.accumulate) { mix_l = prm.out[p - prm.p_begin] + mix_l; mix_r = prm.out[prm.out_stride + p - prm.p_begin] + mix_r; }
         prm.out[p - prm.p_begin] = mix_l;
         prm.out[prm.out_stride + p - prm.p_begin] = mix_r;
     }
@@ -123,6 +124,7 @@ extern "C" int bas_render(const float* x_dev, long long x_stride, long long n_va
                           float* peaks_dev, int variant, void* workspace_dev, long long workspace_bytes, void* stream) {
     BAS_CHECK_ARG(x_dev && filt_dev && out_dev, "null pointer");
     BAS_CHECK_ARG(n_src >= 1, "n_src");
+    BAS_CHECK_ARG(mix == 0 || mix == 1 || mix == BAS_MIX_ACCUMULATE, "mix must be 0, 1 or BAS_MIX_ACCUMULATE");
     BAS_CHECK_ARG(C >= 1 && S >= 1 && C % S == 0, "subchunksize must divide chunksize");     // apply_hrtf.py:401-402
     BAS_CHECK_ARG(K >= 1 && K < (1 << 20), "K");
     BAS_CHECK_ARG(n_in >= C && n_in % C == 0, "n_in must be a positive multiple of C");      // apply_hrtf.py:405
@@ -138,7 +140,7 @@ extern "C" int bas_render(const float* x_dev, long long x_stride, long long n_va
     prm.pitch = bas_filter_row_pitch(K);
     prm.filt_src_stride = (n_in / C + 1) * (long long)prm.pitch;
     prm.gains = gains_dev; prm.p_begin = p_begin; prm.p_end = p_begin + p_count;
-    prm.out = out_dev; prm.out_stride = out_stride; prm.mix = mix ? 1 : 0; prm.peaks = peaks_dev; prm.tiles = 0;
+    prm.out = out_dev; prm.out_stride = out_stride; prm.mix = mix ? 1 : 0; prm.accumulate = mix == BAS_MIX_ACCUMULATE ? 1 : 0; prm.peaks = peaks_dev; prm.tiles = 0;
 
     const int base = variant & 0x3f;
     BAS_CHECK_ARG(base == BAS_RENDER_AUTO || base == BAS_RENDER_GENERIC || base == BAS_RENDER_TILED, "variant");

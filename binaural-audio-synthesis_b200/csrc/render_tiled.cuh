@@ -16,6 +16,7 @@ struct RenderParams {
     long long p_begin, p_end;      // rendered output range [p_begin, p_end)
     float* out; long long out_stride;
     int mix;
+    int accumulate;                // mix only: add to what `out` already holds (source groups rendered in turn)
     float* peaks;
     long long tiles;               // tiled kernel: tiles per source
     int parts;                     // tiled kernel: warps that share one 1024-output stripe (split along the taps)
@@ -531,6 +532,12 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
                             unpack2(acc[r4 + i], l[i], rr[i]);
                             if (!MIX) { l[i] *= gain; rr[i] *= gain; }
                         }
+                        if (MIX && prm.accumulate) {            // earlier source groups first, then this one
+                            const float4 ol = *reinterpret_cast<const float4*>(o + off + r4);
+                            const float4 orr = *reinterpret_cast<const float4*>(o + prm.out_stride + off + r4);
+                            l[0] = ol.x + l[0]; l[1] = ol.y + l[1]; l[2] = ol.z + l[2]; l[3] = ol.w + l[3];
+                            rr[0] = orr.x + rr[0]; rr[1] = orr.y + rr[1]; rr[2] = orr.z + rr[2]; rr[3] = orr.w + rr[3];
+                        }
                         *reinterpret_cast<float4*>(o + off + r4) = make_float4(l[0], l[1], l[2], l[3]);
                         *reinterpret_cast<float4*>(o + prm.out_stride + off + r4) = make_float4(rr[0], rr[1], rr[2], rr[3]);
                     }
@@ -539,7 +546,10 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
                     for (int r = 0; r < kBlk; ++r) {
                         float l, rr; unpack2(acc[r], l, rr);
                         if (!MIX) { l *= gain; rr *= gain; }
-                        if (pb + r >= prm.p_begin && pb + r < prm.p_end) { o[off + r] = l; o[prm.out_stride + off + r] = rr; }
+                        if (pb + r >= prm.p_begin && pb + r < prm.p_end) {
+                            if (MIX && prm.accumulate) { l = o[off + r] + l; rr = o[prm.out_stride + off + r] + rr; }
+                            o[off + r] = l; o[prm.out_stride + off + r] = rr;
+                        }
                     }
                 }
             }

@@ -137,7 +137,9 @@ int bas_filter_row_pitch(int K);
  * gains_dev: n_src floats multiplying each source before mixing, or NULL for 1.
  * Output samples p_begin <= p < p_begin + p_count (0 <= p, p_begin + p_count <= n_in + K - 1):
  * out_dev:   mix=0: n_src x 2 x out_stride (planar L then R), out[s][e][p - p_begin];
- *            mix=1: 2 x out_stride holding the gain-weighted sum over sources (deterministic order).
+ *            mix=1: 2 x out_stride holding the gain-weighted sum over sources (deterministic order);
+ *            mix=BAS_MIX_ACCUMULATE: the same sum ADDED to what out_dev already holds, so that groups
+ *            of sources can be rendered in turn (earlier groups first) into one mix.
  * peaks_dev: n_src floats, max |out| of each source over the rendered range BEFORE gain and mixing
  *            (for apply_hrtf.py:462), or NULL.  Must be zeroed by the caller (atomic max).
  * variant:   BAS_RENDER_AUTO / _GENERIC (any C, S, K) / _TILED (needs S == 32, C % 32 == 0,
@@ -146,6 +148,7 @@ int bas_filter_row_pitch(int K);
 #define BAS_RENDER_AUTO 0
 #define BAS_RENDER_GENERIC 1
 #define BAS_RENDER_TILED 2
+#define BAS_MIX_ACCUMULATE 2
 #define BAS_RENDER_SPLIT 0x40       /* OR-ed into variant: always balance by splitting tiles between CTAs */
 #define BAS_RENDER_NO_SPLIT 0x80    /* OR-ed into variant: never split a tile between CTAs */
 int bas_render(const float* x_dev, long long x_stride, long long n_valid, int n_src, long long n_in,

@@ -105,3 +105,31 @@ def test_config5_full_length_irs_n16_bank(bas, oracle):
     twice = bas.render_sources(2.0 * x[:3], 512, 32, trajs[:3], bank, variant=shape)
     assert np.array_equal(twice, 2.0 * once)
     assert rel_l2(once, each[:3]) <= 1e-6
+
+
+def test_grouped_mix_equals_one_launch(bas, synth_bank, monkeypatch):
+    """Mixing more than MIX_GROUP_SOURCES device-resident sources runs as groups: plan + ir_synth of the
+    next group on a side stream while the previous group renders, every later group ADDED to the mix
+    (BAS_MIX_ACCUMULATE).  Same mix as the one-launch path up to the order of the group sums."""
+    import torch
+    ah = bas.apply_hrtf
+    fs, n_src, n = 44100, 37, 40_000
+    rng = np.random.default_rng(8)
+    x = (0.01 * rng.standard_normal((n_src, n))).astype(np.float32)
+    x[20] *= 300.0                                             # one source that is normalised on its own (gains pass)
+    trajs = [_lissajous(fs, 200 + s) for s in range(n_src)]
+    xd = torch.zeros((n_src, (n + 511) // 512 * 512), dtype=torch.float32, device='cuda')
+    xd[:, :n] = torch.from_numpy(x).cuda()
+    monkeypatch.setattr(ah, 'MIX_GROUP_SOURCES', 1000)
+    one, peaks_one = ah.render_sources(xd, 512, 32, trajs, synth_bank, mix=True, return_device=True, return_peaks=True)
+    one = one.cpu().numpy()
+    for group in (8, 16):
+        monkeypatch.setattr(ah, 'MIX_GROUP_SOURCES', group)
+        got, peaks = ah.render_sources(xd, 512, 32, trajs, synth_bank, mix=True, return_device=True, return_peaks=True)
+        assert np.array_equal(peaks, peaks_one) and peaks[20] > 1
+        assert rel_l2(got.cpu().numpy(), one) <= 1e-6
+    # a failing direction in a later group is reported with its source
+    bad = list(trajs)
+    bad[30] = lambda t: (0.0, float('nan'))
+    with pytest.raises(AssertionError, match='source 30'):
+        ah.render_sources(xd, 512, 32, bad, synth_bank, mix=True, return_device=True)
