@@ -99,6 +99,7 @@ def _load():
         'bas_pipeline_trace': ([i, C.c_char_p, C.c_size_t], i),
         'bas_memset': ([vp, i, ll, vp], i),
         'bas_probe_clock': ([i, i, i, i, vp, vp, vp], i),
+        'bas_probe_block': ([i, i, i, vp, vp], i),
         'bas_probe_fma': ([i, i, i, i, vp, vp], i),
     }
     for name, (argtypes, restype) in sigs.items():

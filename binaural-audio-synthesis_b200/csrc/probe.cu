@@ -193,3 +193,58 @@ extern "C" int bas_probe_clock(int packed, int blocks, int threads, int iters, f
     BAS_LAUNCH_CHECK();
     return 0;
 }
+
+// ---- the render kernel's own 32x32 block (render_tiled.cuh: block_diag) on synthetic shared-memory data,
+//      without the tile machinery around it: how fast the block itself can go --------------------------
+#include "render_tiled.cuh"
+
+namespace {
+using namespace bas_render_detail;
+
+// per warp: 34 input rows on the 144-byte pitch, and two filter rows of 2 x 258 taps
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
+bas_probe_block_kernel(int iters, int blocks_per_iter, float* __restrict__ sink) {
+    extern __shared__ __align__(16) unsigned char psm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pitch = 258;
+    float2* rows = reinterpret_cast<float2*>(psm);                       // [4 rows][pitch], shared by the CTA
+    float* xw = reinterpret_cast<float*>(psm + 4 * pitch * 8) + warp * 72 * kXPitch;   // 72 rows per warp
+    for (int i = threadIdx.x; i < 4 * pitch; i += blockDim.x) rows[i] = make_float2(1e-3f * (i % 97), -1e-3f * (i % 89));
+    for (int i = lane; i < 72 * kXPitch; i += 32) xw[i] = 1e-2f * (i % 31);
+    __syncthreads();
+    u64 acc[kBlk];
+#pragma unroll
+    for (int r = 0; r < kBlk; ++r) acc[r] = 0ull;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll 1
+        for (int d = 0; d < blocks_per_iter; ++d) {
+            const int chunk = (lane + d) & 1;                             // lanes read two different filter rows
+            const float2* ra = rows + chunk * pitch + 32 * d + 32;        // taps base - 31 .. base + 31 inside the row
+            const float alpha = 0.0625f * ((lane + it) & 15);
+            const u64 aa = pack2(alpha, alpha);
+            const float* xa = xw + (lane + 8 - d) * kXPitch;
+            block_diag(acc, ra, aa, ra, aa, pitch, xa, xa);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < kBlk; ++r) { float l, rr; unpack2(acc[r], l, rr); s += l + rr; }
+    sink[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+}  // namespace
+
+// blocks CTAs of 128 threads, each warp running iters x 6 blocks (6 x 1024 useful packed FMAs per lane per iteration).
+extern "C" int bas_probe_block(int ctas_per_sm, int blocks, int iters, float* sink_dev, void* stream) {
+    BAS_CHECK_ARG(sink_dev && blocks >= 1 && iters >= 1 && ctas_per_sm >= 1 && ctas_per_sm <= 3, "launch shape");
+    const size_t smem = 4 * 258 * 8 + 4 * 72 * kXPitch * 4;
+    if (ctas_per_sm == 3) {
+        BAS_CUDA(cudaFuncSetAttribute(bas_probe_block_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        bas_probe_block_kernel<3><<<blocks, 128, smem, (cudaStream_t)stream>>>(iters, 6, sink_dev);
+    } else {
+        BAS_CUDA(cudaFuncSetAttribute(bas_probe_block_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        bas_probe_block_kernel<2><<<blocks, 128, smem, (cudaStream_t)stream>>>(iters, 6, sink_dev);
+    }
+    BAS_LAUNCH_CHECK();
+    return 0;
+}

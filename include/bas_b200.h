@@ -248,6 +248,11 @@ int bas_probe_fma(int packed, int blocks, int threads, int iters, float* sink_de
  * device (clock64 against the nanosecond global timer): what the FMA peak has to be read against. */
 int bas_probe_clock(int packed, int blocks, int threads, int iters, float* sink_dev, float* mhz_dev, void* stream);
 
+/* The render kernel's own 32x32 block on synthetic shared-memory data, without the tile machinery:
+ * `blocks` CTAs of 4 warps, every warp runs iters x 6 blocks of 1024 useful packed FMAs per lane.
+ * ctas_per_sm (1..3) selects the register budget the block is compiled for. */
+int bas_probe_block(int ctas_per_sm, int blocks, int iters, float* sink_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
