@@ -56,6 +56,7 @@ N = 4
 t_s = timed(lambda: [synth(s0, 1) for _ in range(N)])
 t_r = timed(lambda: [render(s0, 0) for _ in range(N)])
 t_both = timed(lambda: [(synth(s1, 1), render(s0, 0)) for _ in range(N)])
+t_both_r = timed(lambda: [(render(s0, 0), synth(s1, 1)) for _ in range(N)])
 t_both_hi = None
-print('variant %#x: %d x synth %.3f ms, %d x render %.3f ms, serial sum %.3f ms, two streams %.3f ms' % (
-    variant, N, t_s, N, t_r, t_s + t_r, t_both))
+print('variant %#x: %d x synth %.3f ms, %d x render %.3f ms, serial sum %.3f ms, two streams %.3f ms (synth issued first) / %.3f ms (render issued first)' % (
+    variant, N, t_s, N, t_r, t_s + t_r, t_both, t_both_r))
