@@ -78,6 +78,24 @@ def make_bank(bas):
     return bank
 
 
+def pin_to_device_cpus(index):
+    """Run this rank on the CPU cores NVML names as local to GPU `index` (same NUMA node / PCIe root):
+    the pinned host buffers of the e2e leg are then allocated next to the GPU they feed."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return 'rank pinned to the %d CPU cores local to its GPU (NVML)' % len(cpus)
+    except Exception as e:
+        return 'cpu affinity not set (%s)' % type(e).__name__
+    return None
+
+
 class ClockSampler:
     """SM clock and throttle reasons of one GPU while the timed region runs (NVML, ~2 ms period)."""
 
@@ -186,6 +204,7 @@ def run_ours(args, rank, local_rank, world):
     lib = _cabi.lib
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    cpu_note = pin_to_device_cpus(local_rank) if world > 1 and not os.environ.get('BAS_NO_CPU_AFFINITY') else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -377,7 +396,7 @@ def run_ours(args, rank, local_rank, world):
                    'd2h_bytes_per_step': int(8 * n_out + 12), 'ms_per_step': 1e3 * dt, 'steps': e2e_steps,
                    'call': 'make_signal_move_2d(host float32 ndarray, 512, 32, vectorised trajectory, bank) -> host ndarray, '
                            'one call per rank per step, wall clock, max over ranks',
-                   'n_gpus': world}
+                   'n_gpus': world, 'cpu_affinity': cpu_note}
 
     if rank == 0:
         # ---- CPU baseline: numpy port of the reference, one core, first seconds of the workload ----
