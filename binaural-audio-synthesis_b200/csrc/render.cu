@@ -192,7 +192,7 @@ extern "C" int bas_render(const float* x_dev, long long x_stride, long long n_va
                     }
                     const int wps = (ctas * sh.tw + 3) / 4;
                     double cost = waves * blocks_per_tile * wps;
-                    cost *= 1.0 + 0.16 * (parts - 1) + (sh.ns == 1 && ctas == 1 ? 0.02 : 0.0) + (wps < 2 ? 0.3 : 0.0) +
+                    cost *= 1.0 + 0.25 * (parts - 1) + (sh.ns == 1 && ctas == 1 ? 0.02 : 0.0) + (wps < 2 ? 0.3 : 0.0) +
                             (prm.mix ? (sh.tw == 8 ? -0.05 : sh.minb == 3 ? 0.03 : 0.0) : (sh.tw == 4 ? 0.0 : 0.05));
                     if (!best || cost < best_cost) { best = &sh; best_parts = parts; best_cost = cost; }
                 }
