@@ -224,7 +224,7 @@ bas_probe_block_kernel(int iters, int blocks_per_iter, float* __restrict__ sink)
             const float alpha = 0.0625f * ((lane + it) & 15);
             const u64 aa = pack2(alpha, alpha);
             const float* xa = xw + (lane + 8 - d) * kXPitch;
-            block_diag(acc, ra, aa, ra, aa, pitch, xa, xa);
+            block_diag(acc, ra, aa, ra, aa, pitch, xa, 0, xa, 0);
         }
     }
     float s = 0.f;

@@ -17,12 +17,12 @@
 // Tiled kernel
 //   work     A CTA of TW warps owns tiles of TW*1024 consecutive outputs (one 1024-output stripe
 //            per warp) and walks over its tiles persistently (grid = resident CTAs).
-//   staging  For every (tile, source) item one warp issues cp.async.bulk (TMA, 1-D) copies into a
-//            two-stage shared-memory ring guarded by full/empty mbarriers: the input samples as
-//            128-byte rows on a 144-byte pitch (conflict-free for the lane-per-row reads below) and
-//            the boundary-filter rows of the chunks the tile touches as ONE contiguous copy (rows
-//            come from ir_synth already interleaved {L,R} and zero padded).  The copy of item j+1
-//            overlaps the arithmetic of item j; there is no __syncthreads in the kernel.
+//   staging  For every (tile, source) item one thread issues TMA copies into a shared-memory ring guarded
+//            by full/empty mbarriers: the input samples as a tiled tensor-map copy with the 128-byte
+//            swizzle (rows outside the signal arrive as zeros; lane-per-row reads are conflict free
+//            through the XOR), and the boundary-filter rows of the chunks the tile touches as ONE
+//            contiguous bulk copy (rows come from ir_synth already interleaved {L,R} and zero padded).
+//            There is no __syncthreads in the kernel.
 //   math     Lane l of a warp owns the 32 consecutive outputs of block b = b0 + l for both ears: 32
 //            fma.rn.f32x2 accumulators {L,R}.  Output block b draws on input subchunks q = b - d:
 //                out[32b + r] += x[32q + m] * h_q[32d + r - m]          r, m = 0..31
@@ -39,6 +39,7 @@
 
 #include <atomic>
 #include <chrono>
+#include <stdlib.h>
 
 using namespace bas_render_detail;
 
@@ -140,7 +141,7 @@ extern "C" int bas_render(const float* x_dev, long long x_stride, long long n_va
     prm.pitch = bas_filter_row_pitch(K);
     prm.filt_src_stride = (n_in / C + 1) * (long long)prm.pitch;
     prm.gains = gains_dev; prm.p_begin = p_begin; prm.p_end = p_begin + p_count;
-    prm.out = out_dev; prm.out_stride = out_stride; prm.mix = mix ? 1 : 0; prm.accumulate = mix == BAS_MIX_ACCUMULATE ? 1 : 0; prm.peaks = peaks_dev; prm.tiles = 0;
+    prm.out = out_dev; prm.out_stride = out_stride; prm.mix = mix ? 1 : 0; prm.accumulate = mix == BAS_MIX_ACCUMULATE ? 1 : 0; prm.peaks = peaks_dev; prm.tiles = 0; prm.parts = 1; prm.tmap = 0; prm.box_rows = 0; prm.n_box = 0;
 
     const int base = variant & 0x3f;
     BAS_CHECK_ARG(base == BAS_RENDER_AUTO || base == BAS_RENDER_GENERIC || base == BAS_RENDER_TILED, "variant");
@@ -161,6 +162,7 @@ extern "C" int bas_render(const float* x_dev, long long x_stride, long long n_va
         const long long p_base = p_begin / kBlk * kBlk;
         const bool split = (variant & BAS_RENDER_SPLIT) || (prm.mix && !(variant & BAS_RENDER_NO_SPLIT));
         const bool can_split = split && workspace_dev != nullptr;
+        const bool use_tmap = input_tensor_map_possible(prm);
         const TiledShape* best = nullptr;
         int best_parts = 0;
         double best_cost = 0.0;
@@ -173,7 +175,7 @@ extern "C" int bas_render(const float* x_dev, long long x_stride, long long n_va
                 for (int parts = 1; parts <= sh.tw && parts <= 8; ++parts) {
                     if (sh.tw % parts || (parts_req && parts != parts_req)) continue;
                     if (!parts_req && parts > D) continue;                  // nothing left to share
-                    const int ctas = sh.ctas_per_sm[mixi](K, C, prm.pitch, parts);
+                    const int ctas = sh.ctas_per_sm[mixi](K, C, prm.pitch, parts, use_tmap);
                     if (ctas < 1) continue;
                     // Measured on B200 (tools/tune_render.py): every shape that keeps 8 or 12 warps per SM
                     // busy lands within a few per cent; what separates them is how evenly the tiles of
@@ -216,6 +218,43 @@ extern "C" int bas_render(const float* x_dev, long long x_stride, long long n_va
 }
 
 namespace bas_render_detail {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (getenv("BAS_NO_TMAP")) return (EncodeTiledFn) nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return (EncodeTiledFn) nullptr;
+        }
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+bool input_tensor_map_possible(const RenderParams& prm) {
+    return encode_tiled_fn() != nullptr && prm.n_valid >= kBlk && prm.n_valid % kBlk == 0 &&
+           (reinterpret_cast<uintptr_t>(prm.x) & 15) == 0 && (prm.n_src == 1 || prm.x_stride % 4 == 0) &&
+           prm.n_valid / kBlk < (1LL << 31) && prm.n_src < (1 << 30);
+}
+
+bool make_input_tensor_map(CUtensorMap* map, const RenderParams& prm, int box_rows) {
+    if (!input_tensor_map_possible(prm) || box_rows < 1 || box_rows > 256) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)kBlk, (cuuint64_t)(prm.n_valid / kBlk), (cuuint64_t)prm.n_src};
+    const cuuint64_t source_stride = (cuuint64_t)(prm.n_src == 1 ? prm.n_valid : prm.x_stride) * 4;
+    const cuuint64_t strides[2] = {(cuuint64_t)kBlk * 4, source_stride};
+    const cuuint32_t box[3] = {(cuuint32_t)kBlk, (cuuint32_t)box_rows, 1u};
+    const cuuint32_t elem[3] = {1u, 1u, 1u};
+    const CUresult rc = encode_tiled_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(prm.x), dims, strides, box, elem,
+                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return rc == CUDA_SUCCESS;
+}
+
 unsigned long long next_epoch() {
     static std::atomic<unsigned long long> counter{0};
     static const unsigned long long salt = [] {

@@ -3,6 +3,8 @@
 #pragma once
 #include "bas_internal.cuh"
 
+#include <cuda.h>
+
 namespace bas_render_detail {
 
 struct RenderParams {
@@ -20,6 +22,8 @@ struct RenderParams {
     float* peaks;
     long long tiles;               // tiled kernel: tiles per source
     int parts;                     // tiled kernel: warps that share one 1024-output stripe (split along the taps)
+    int tmap;                      // tiled kernel: input rows arrive by tensor-map TMA (128-byte swizzle), else bulk copy + re-layout
+    int box_rows, n_box;           // tensor-map path: rows per copy, copies per item
 };
 
 __device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
@@ -96,6 +100,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// TMA tiled copy of a (32 floats x box_rows x 1) box of the input tensor [source][row][32]; rows outside
+// the signal (negative or past the end) arrive as zeros; 128-byte swizzle (UTMALDG in SASS)
+__device__ __forceinline__ void tensor_g2s(void* dst_smem, const CUtensorMap* map, int row, int src, void* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst_smem)), "l"(map), "r"(0), "r"(row), "r"(src), "r"(smem_u32(bar)) : "memory");
+}
+
 constexpr int kBlk = 32;                 // outputs per lane = subchunk size of the tiled kernel
 constexpr int kWarpTile = 32 * kBlk;     // 1024 outputs per warp
 constexpr int kXPitch = 36;              // floats per staged input row (32 samples + 16 bytes)
@@ -126,9 +137,17 @@ constexpr size_t kBarBytes = 64;         // full + empty mbarriers of up to 2 st
 constexpr size_t kStripeBytes = (size_t)kWarpTile * 8;      // one stripe of {L,R} partial sums
 // barriers | NS stages | per-warp input rows | blend weights per subchunk | partial sums of the warps
 // that share a stripe (parts > 1) | mix accumulators (MIX, one stripe per part-0 warp)
-__host__ __device__ inline size_t tile_smem_bytes(const TileGeom& g, int TW, int NS, int parts, int C, bool mix) {
+// tensor-map path: the rows of an item land densely (128-byte pitch, swizzled) in n_box copies of box_rows rows
+__host__ __device__ inline int tmap_n_box(int x_rows) { return (x_rows + 255) / 256; }
+__host__ __device__ inline int tmap_box_rows(int x_rows) { const int n = tmap_n_box(x_rows); return (x_rows + n - 1) / n; }
+__host__ __device__ inline size_t tmap_stage_bytes(const TileGeom& g) {
+    const size_t x = (size_t)tmap_n_box(g.x_rows) * tmap_box_rows(g.x_rows) * 128;
+    return (x + g.f_bytes + 1023) / 1024 * 1024;                  // every stage starts on a swizzle atom
+}
+__host__ __device__ inline size_t tile_smem_bytes(const TileGeom& g, int TW, int NS, int parts, int C, bool mix, bool tmap) {
     const int TS = TW / parts;
-    return kBarBytes + (size_t)NS * g.stage_bytes + (size_t)TW * g.warp_x_bytes + (size_t)((C / kBlk * 4 + 15) / 16 * 16) +
+    const size_t staging = tmap ? 1024 + (size_t)NS * tmap_stage_bytes(g) : (size_t)NS * g.stage_bytes + (size_t)TW * g.warp_x_bytes;
+    return kBarBytes + staging + (size_t)((C / kBlk * 4 + 15) / 16 * 16) +
            (parts > 1 ? (size_t)(TW - TS) * kStripeBytes : 0) + (mix ? (size_t)TS * kStripeBytes : 0);
 }
 
@@ -144,11 +163,13 @@ __host__ __device__ inline size_t tile_smem_bytes(const TileGeom& g, int TW, int
 // diagonal overlap the FMAs of the current one, so a block has no serial prologue.
 __device__ __forceinline__ void block_diag(u64 (&acc)[kBlk], const float2* __restrict__ ra, u64 alpha_a,
                                            const float2* __restrict__ rb, u64 alpha_b, int pitch,
-                                           const float* __restrict__ xa, const float* __restrict__ xb) {
+                                           const float* __restrict__ xa, int ka, const float* __restrict__ xb, int kb) {
+    // xa / xb: the lane's input row; 16-byte chunk m4 of a row sits at chunk (m4 ^ key): key = row & 7 in the
+    // swizzled tensor-map layout, 0 on the padded pitch
     float x[kBlk];
 #pragma unroll
     for (int m4 = 0; m4 < kBlk / 4; ++m4) {
-        const float4 v = *reinterpret_cast<const float4*>(xa + 4 * m4);
+        const float4 v = *reinterpret_cast<const float4*>(xa + 4 * (m4 ^ ka));
         x[4 * m4] = v.x; x[4 * m4 + 1] = v.y; x[4 * m4 + 2] = v.z; x[4 * m4 + 3] = v.w;
     }
 #pragma unroll
@@ -164,7 +185,7 @@ __device__ __forceinline__ void block_diag(u64 (&acc)[kBlk], const float2* __res
     }
 #pragma unroll
     for (int m4 = 0; m4 < kBlk / 4; ++m4) {      // folded block: the d = D part reads another input row
-        const float4 v = *reinterpret_cast<const float4*>(xb + 4 * m4);
+        const float4 v = *reinterpret_cast<const float4*>(xb + 4 * (m4 ^ kb));
         x[4 * m4] = v.x; x[4 * m4 + 1] = v.y; x[4 * m4 + 2] = v.z; x[4 * m4 + 3] = v.w;
     }
 #pragma unroll
@@ -233,20 +254,25 @@ __device__ __forceinline__ void cta_barrier(int threads) {
 // whose tile count is a small multiple of the resident warps.
 template <int TW, bool MIX, int NS, int MINB>
 __global__ void __launch_bounds__(TW * 32, MINB)
-bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ workspace) {
+bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ workspace, const __grid_constant__ CUtensorMap xmap) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int P = prm.parts, TS = TW / P;
     const TileGeom g = tile_geom(prm.K, prm.C, prm.pitch, TS);
     u64* full_bar = reinterpret_cast<u64*>(smem);              // [NS]
     u64* empty_bar = full_bar + NS;                       // [NS]
+    // tensor-map path: stages start on a 1024-byte boundary (the 128-byte swizzle works on address bits)
+    const bool tmap = prm.tmap != 0;
     unsigned char* stage_base = smem + kBarBytes;
+    if (tmap) stage_base += (1024u - (smem_u32(stage_base) & 1023u)) & 1023u;
+    const size_t stage_stride = tmap ? tmap_stage_bytes(g) : (size_t)g.stage_bytes;
+    const size_t x_stage_bytes = tmap ? (size_t)prm.n_box * prm.box_rows * 128 : (size_t)g.x_bytes;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int stripe = warp / P, part = warp - stripe * P;     // warps of a stripe are neighbours
     const int spc = prm.C / kBlk;                              // subchunks per chunk
-    unsigned char* after_stages = stage_base + (size_t)NS * g.stage_bytes;
-    float* xw = reinterpret_cast<float*>(after_stages + (size_t)warp * g.warp_x_bytes);
-    float* alpha_tab = reinterpret_cast<float*>(after_stages + (size_t)TW * g.warp_x_bytes);
+    unsigned char* after_stages = stage_base + (size_t)NS * stage_stride;
+    float* xw = reinterpret_cast<float*>(after_stages + (size_t)warp * g.warp_x_bytes);          // unused on the tensor-map path
+    float* alpha_tab = reinterpret_cast<float*>(after_stages + (tmap ? 0 : (size_t)TW * g.warp_x_bytes));
     unsigned char* after_alpha = reinterpret_cast<unsigned char*>(alpha_tab) + (spc * 4 + 15) / 16 * 16;
     // partial sums of parts 1..P-1 of every stripe: [stripe][part - 1][r][lane] {L,R}
     u64* red = reinterpret_cast<u64*>(after_alpha);
@@ -329,18 +355,27 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
             const Item it = item_info(j);
             long long n_lo, c_first; int n_rows;
             tile_chunks(it.tile, n_lo, c_first, n_rows);
-            float* xs = reinterpret_cast<float*>(stage_base + (size_t)st * g.stage_bytes);
-            float2* fs = reinterpret_cast<float2*>(stage_base + (size_t)st * g.stage_bytes + g.x_bytes);
+            float* xs = reinterpret_cast<float*>(stage_base + (size_t)st * stage_stride);
+            float2* fs = reinterpret_cast<float2*>(stage_base + (size_t)st * stage_stride + x_stage_bytes);
             const float* x = prm.x + (long long)it.src * prm.x_stride;
-            // two bulk copies per item: the in-range part of the input span, and the filter rows.
-            // Samples outside [0, n_valid) are never copied; consumers zero them while re-laying out.
-            const long long na = n_lo < 0 ? 0 : n_lo;
-            long long nb = n_lo + (long long)g.x_rows * kBlk;
-            if (nb > prm.n_valid) nb = prm.n_valid;
-            const unsigned x_bytes = nb > na ? (unsigned)(nb - na) * 4 : 0;
             const unsigned f_bytes = (unsigned)n_rows * prm.pitch * 8;
-            mbar_arrive_expect_tx(full_bar + st, x_bytes + f_bytes);
-            if (x_bytes) bulk_g2s(xs + (na - n_lo), x + na, x_bytes, full_bar + st);
+            if (tmap) {
+                // input rows: n_box tiled copies of box_rows rows each (rows outside the signal are zero-filled by
+                // the TMA unit, and count towards the transaction bytes); filter rows: one bulk copy
+                mbar_arrive_expect_tx(full_bar + st, (unsigned)x_stage_bytes + f_bytes);
+                const int row0 = (int)(n_lo / kBlk);                           // exact, may be negative
+                for (int b = 0; b < prm.n_box; ++b)
+                    tensor_g2s(reinterpret_cast<unsigned char*>(xs) + (size_t)b * prm.box_rows * 128, &xmap, row0 + b * prm.box_rows, it.src, full_bar + st);
+            } else {
+                // two bulk copies per item: the in-range part of the input span, and the filter rows.
+                // Samples outside [0, n_valid) are never copied; consumers zero them while re-laying out.
+                const long long na = n_lo < 0 ? 0 : n_lo;
+                long long nb = n_lo + (long long)g.x_rows * kBlk;
+                if (nb > prm.n_valid) nb = prm.n_valid;
+                const unsigned x_bytes = nb > na ? (unsigned)(nb - na) * 4 : 0;
+                mbar_arrive_expect_tx(full_bar + st, x_bytes + f_bytes);
+                if (x_bytes) bulk_g2s(xs + (na - n_lo), x + na, x_bytes, full_bar + st);
+            }
             bulk_g2s(fs, prm.filt + (long long)it.src * prm.filt_src_stride + c_first * prm.pitch, f_bytes, full_bar + st);
         }
         __syncwarp();
@@ -369,8 +404,8 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
         tile_chunks(it.tile, n_lo, c_first, n_rows);
         const long long P0 = p_base + it.tile * T;
         const bool warp_live = P0 + (long long)stripe * kWarpTile < prm.p_end;
-        const float* xs = reinterpret_cast<const float*>(stage_base + (size_t)st * g.stage_bytes);
-        const float2* fs = reinterpret_cast<const float2*>(stage_base + (size_t)st * g.stage_bytes + g.x_bytes);
+        const float* xs = reinterpret_cast<const float*>(stage_base + (size_t)st * stage_stride);
+        const float2* fs = reinterpret_cast<const float2*>(stage_base + (size_t)st * stage_stride + x_stage_bytes);
         const long long q0 = n_lo / kBlk;                       // exact (n_lo % 32 == 0), may be negative
         // this warp's share of the item's tap blocks
         const int len = it.d1 - it.d0;
@@ -379,18 +414,20 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
         mbar_wait(full_bar + st, (unsigned)((j / NS) & 1));
 
         if (warp_live && d_last > d_first) {
-            // re-lay this warp's input rows from the linear staging buffer onto the 144-byte pitch
-            // (lane-per-row reads below are then conflict free) and zero what lies outside the signal
-            const long long n_w = n_lo + (long long)stripe * kWarpTile;
-            const float4* lin = reinterpret_cast<const float4*>(xs) + stripe * (kWarpTile / 4);
-            for (int idx = lane; idx < g.w_rows * 8; idx += 32) {
-                const int row = idx >> 3, ch = idx & 7;
-                const long long n = n_w + (long long)row * kBlk + ch * 4;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (n >= 0 && n + 4 <= prm.n_valid) v = lin[idx];
-                *reinterpret_cast<float4*>(xw + row * kXPitch + ch * 4) = v;
+            if (!tmap) {
+                // re-lay this warp's input rows from the linear staging buffer onto the 144-byte pitch
+                // (lane-per-row reads below are then conflict free) and zero what lies outside the signal
+                const long long n_w = n_lo + (long long)stripe * kWarpTile;
+                const float4* lin = reinterpret_cast<const float4*>(xs) + stripe * (kWarpTile / 4);
+                for (int idx = lane; idx < g.w_rows * 8; idx += 32) {
+                    const int row = idx >> 3, ch = idx & 7;
+                    const long long n = n_w + (long long)row * kBlk + ch * 4;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (n >= 0 && n + 4 <= prm.n_valid) v = lin[idx];
+                    *reinterpret_cast<float4*>(xw + row * kXPitch + ch * 4) = v;
+                }
+                __syncwarp();
             }
-            __syncwarp();
             // Filter row (chunk) and blend weight of the lane's input row.  Input rows are visited in
             // descending order (xrow = blk + D - d), so (chunk, sub) is divided once per item and then
             // stepped; rows outside the staged range belong to input rows that are all zero (clamped).
@@ -425,7 +462,10 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
                     const float alpha_b = alpha_tab[sub_b];
                     ab = pack2(alpha_b, alpha_b);
                 }
-                block_diag(acc, ra, aa, rb, ab, prm.pitch, xw + (xrow_a - stripe * 32) * kXPitch, xw + (xrow_b - stripe * 32) * kXPitch);
+                // the lane's input rows: on the padded per-warp copy, or in place in the swizzled stage
+                const float* pa = tmap ? xs + xrow_a * kBlk : xw + (xrow_a - stripe * 32) * kXPitch;
+                const float* pb_ = tmap ? xs + xrow_b * kBlk : xw + (xrow_b - stripe * 32) * kXPitch;
+                block_diag(acc, ra, aa, rb, ab, prm.pitch, pa, tmap ? (xrow_a & 7) : 0, pb_, tmap ? (xrow_b & 7) : 0);
                 // next row down: q - 1
                 if (q_top - d - 1 < 0) { chunk = 0; sub = 0; }
                 else if (--sub < 0) { sub = spc - 1; --chunk; }
@@ -563,6 +603,11 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
     }
 }
 
+// Tensor map of the input signals as [source][row][32 floats] with the 128-byte swizzle; false when the
+// signal does not qualify (or the driver entry point is missing): the kernel then stages with bulk copies.
+bool input_tensor_map_possible(const RenderParams& prm);
+bool make_input_tensor_map(CUtensorMap* map, const RenderParams& prm, int box_rows);
+
 // Launch stamp the hand-off flags of a split launch are compared with: unique per launch of this
 // process (random salt in the high bits), so stale flags in the caller's workspace never match.
 unsigned long long next_epoch();
@@ -579,10 +624,10 @@ inline int device_sm_count() {
 
 // Resident CTAs per SM this shape reaches with `parts` warps per stripe (0: does not fit).
 template <int TW, bool MIX, int NS, int MINB>
-int tiled_ctas_per_sm(int K, int C, int pitch, int parts) {
+int tiled_ctas_per_sm(int K, int C, int pitch, int parts, bool tmap) {
     if (parts < 1 || TW % parts) return 0;
     const TileGeom g = tile_geom(K, C, pitch, TW / parts);
-    const size_t smem = tile_smem_bytes(g, TW, NS, parts, C, MIX);
+    const size_t smem = tile_smem_bytes(g, TW, NS, parts, C, MIX, tmap);
     if (smem > 227 * 1024) return 0;
     auto kern = bas_render_tiled_kernel<TW, MIX, NS, MINB>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -596,7 +641,13 @@ int launch_tiled(RenderParams prm, int parts, bool want_split, float* workspace,
     if (parts < 1 || TW % parts) return BAS_E_UNSUPPORTED;
     const int TS = TW / parts;
     const TileGeom g = tile_geom(prm.K, prm.C, prm.pitch, TS);
-    const size_t smem = tile_smem_bytes(g, TW, NS, parts, prm.C, MIX);
+    // input rows by tensor-map TMA when the signal allows it (whole 32-sample rows, 16-byte aligned)
+    CUtensorMap xmap;
+    memset(&xmap, 0, sizeof(xmap));
+    prm.n_box = tmap_n_box(g.x_rows);
+    prm.box_rows = tmap_box_rows(g.x_rows);
+    prm.tmap = make_input_tensor_map(&xmap, prm, prm.box_rows) ? 1 : 0;
+    const size_t smem = tile_smem_bytes(g, TW, NS, parts, prm.C, MIX, prm.tmap != 0);
     if (smem > 227 * 1024) return BAS_E_UNSUPPORTED;
     auto kern = bas_render_tiled_kernel<TW, MIX, NS, MINB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -623,7 +674,7 @@ int launch_tiled(RenderParams prm, int parts, bool want_split, float* workspace,
     const long long need = (long long)ws_bytes(grid, TS);
     sp.split = (want_split && workspace && workspace_bytes >= need && grid > 1 && sp.total / grid >= sp.gs + 1) ? 1 : 0;
     sp.epoch = sp.split ? next_epoch() : 0ull;
-    kern<<<(unsigned)grid, TW * 32, smem, st>>>(prm, sp, workspace);
+    kern<<<(unsigned)grid, TW * 32, smem, st>>>(prm, sp, workspace, xmap);
     e = cudaGetLastError();
     if (e != cudaSuccess) { bas_set_error("bas_render: tiled launch failed: %s", cudaGetErrorString(e)); return (int)e; }
     return 0;
@@ -633,7 +684,7 @@ int launch_tiled(RenderParams prm, int parts, bool want_split, float* workspace,
 // [0] = one source per tile, [1] = mixing.
 struct TiledShape {
     int tw, ns, minb;
-    int (*ctas_per_sm[2])(int K, int C, int pitch, int parts);
+    int (*ctas_per_sm[2])(int K, int C, int pitch, int parts, bool tmap);
     int (*launch[2])(RenderParams prm, int parts, bool want_split, float* workspace, long long workspace_bytes, cudaStream_t st);
 };
 #define BAS_TILED_SHAPE(TW_, NS_, MINB_)                                                            \
