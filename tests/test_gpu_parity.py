@@ -362,3 +362,34 @@ def test_cli_writes_the_reference_file_name(bas, oracle, golden_bank, tmp_path, 
     assert fs_out == fs and got.dtype == np.float32
     close(got, want)
     assert cli.main([]) == 1                                       # no input file: the reference exits 1 (:570-574)
+
+
+def test_signal_that_is_not_whole_rows_takes_the_bulk_copy_path(bas, synth_bank):
+    """bas_render treats samples >= n_valid as zero.  Whole 32-sample rows arrive by tensor-map TMA
+    (hardware zero fill); any other n_valid (a multiple of 4) takes the bulk-copy + re-layout staging.
+    Both must give the bits of the explicitly zero-padded signal."""
+    import torch
+    lib, cabi = bas._cabi.lib, bas._cabi
+    dev = bas.apply_hrtf._device_bank(synth_bank)
+    rng = np.random.default_rng(99)
+    n, c, k = 5000, 512, 256                               # 5000 = 156 rows + 8 samples
+    n_in = (n + c - 1) // c * c
+    n_out, n_pts = n_in + k - 1, n_in // c + 1
+    x = torch.full((n_in,), 7.0, dtype=torch.float32, device='cuda')            # garbage beyond n must not be read
+    x[:n] = torch.from_numpy((0.05 * rng.standard_normal(n)).astype(np.float32)).cuda()
+    xz = x.clone(); xz[n:] = 0
+    times = np.arange(0, n_in + 1, c)
+    elev, azim = _traj(6)(times) if getattr(_traj(6), 'vectorized', False) else zip(*[_traj(6)(int(t)) for t in times])
+    filt = bas.apply_hrtf._plan_and_synth(torch, dev, torch.tensor(np.asarray(elev, dtype=np.float64)).cuda(),
+                                          torch.tensor(np.asarray(azim, dtype=np.float64)).cuda(), cabi.AZ_F64, n_pts, cabi.IR_ROWS)[0]
+    stride = (n_out + 3) // 4 * 4
+    stream = torch.cuda.current_stream().cuda_stream
+    outs = []
+    for sig, n_valid in ((x, n), (xz, n_in)):
+        out = torch.zeros((2, stride), dtype=torch.float32, device='cuda')
+        peak = torch.zeros(1, dtype=torch.float32, device='cuda')
+        cabi.check(lib.bas_render(sig.data_ptr(), n_in, n_valid, 1, n_in, c, 32, k, filt.data_ptr(), None, 0, n_out, out.data_ptr(),
+                                  stride, 0, peak.data_ptr(), cabi.render_variant(4, 1, 3, 1, False), None, 0, stream), 'bas_render')
+        outs.append((out.cpu().numpy(), float(peak)))
+    assert np.array_equal(outs[0][0], outs[1][0]) and outs[0][1] == outs[1][1]
+    assert np.abs(outs[0][0]).max() > 0
