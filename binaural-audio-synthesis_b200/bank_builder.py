@@ -15,8 +15,8 @@ filter is designed here on the host and handed to the kernels, so either of two 
     'scipy'   scipy.signal.resample_poly's default (Kaiser beta = 5, half length 10 p), which is what
               bank_synth.py has used for the synthetic banks of the tests and benchmarks.
 
-`resample_cpu` / `delay_difference_cpu` are float64 numpy twins of the kernels for the tests.
-There is no CPU fallback in upsample_irs itself.
+There is no CPU path here: the float64 numpy restatements the tests compare the kernels with live in
+`oracle/bank_oracle.py`.
 """
 from __future__ import annotations
 
@@ -57,26 +57,6 @@ def design_filter(p: int, kind: str = 'octave') -> np.ndarray:
     if kind == 'scipy':
         return scipy_filter(p)
     raise ValueError("filter must be 'octave' or 'scipy'")
-
-
-def resample_cpu(x: np.ndarray, p: int, h: np.ndarray) -> np.ndarray:
-    """Zero-phase interpolation by p with the odd-length FIR h: y[m] = sum_k h[Lh + m - k p] x[k]."""
-    x = np.asarray(x, dtype=np.float64)
-    half = (h.size - 1) // 2
-    stuffed = np.zeros(x.size * p)
-    stuffed[::p] = x
-    return np.convolve(stuffed, h)[half:half + x.size * p]
-
-
-def delay_difference_cpu(a: np.ndarray, b: np.ndarray, p: int, h: np.ndarray) -> float:
-    """delaydifference, upsample_irs.m:59-77 with parabolic_interpolation :88-101."""
-    n = a.size
-    cc = np.convolve(np.asarray(a, dtype=np.float64)[::-1], np.asarray(b, dtype=np.float64))      # fftconv(fliplr(a), b)
-    up = resample_cpu(cc, p, h)
-    pk = int(np.argmax(up))                                       # first maximum, 0-based
-    v0, v1, v2 = up[pk - 1], up[pk], up[pk + 1]
-    frac = -(0.5 * (v2 - v0)) / (2 * (0.5 * (v0 + v2 - 2 * v1)))
-    return (pk + 1 + frac - 1) / p - (n - 1)
 
 
 def upsample_irs(l_hrir, r_hrir, upsampling: int, filter: str = 'octave', filename: str | None = None) -> dict:

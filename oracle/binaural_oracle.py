@@ -9,7 +9,7 @@ and `bench.py`'s cpu_baseline / `--impl reference` legs may import it.
 Parity pin: the reference ships no tests or golden vectors, so
 the oracle is pinned against the *live, unmodified reference* imported in the build
 container (`tests/golden/make_golden.py` writes `tests/golden/*.npz`;
-`tests/test_oracle_vs_reference.py` re-checks live when `/root/reference` exists).
+`tests/test_reference_live.py` re-checks live when `/root/reference` exists).
 
 Every function cites the reference lines it restates.  The arithmetic (operation
 order, scalar dtypes, NumPy-2 weak-scalar promotion) follows the reference so that

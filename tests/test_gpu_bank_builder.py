@@ -1,5 +1,6 @@
-"""GPU bank builder (upsample_irs.m on the device) against its float64 numpy twins and
-against the scipy-based restatement that made the synthetic banks of the other tests."""
+"""GPU bank builder (upsample_irs.m on the device) against its float64 numpy oracle
+(oracle/bank_oracle.py) and against the scipy-based restatement that made the synthetic banks of the
+other tests."""
 import numpy as np
 import pytest
 
@@ -8,6 +9,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize('kind', ['octave', 'scipy'])
 def test_small_bank_vs_numpy_twin(bas, kind):
+    from oracle import bank_oracle
     bb = bas.bank_builder
     rng = np.random.default_rng(17)
     n_rows, n, u = 9, 48, 8
@@ -18,13 +20,13 @@ def test_small_bank_vs_numpy_twin(bas, kind):
     h = bb.design_filter(u, kind)
     assert got['upsampling'] == float(u) and got['irs_left'].shape == (n_rows, n * u)
     for ear, x in (('left', left), ('right', right)):
-        want = np.stack([bb.resample_cpu(row, u, h) for row in x])
+        want = np.stack([bank_oracle.resample(row, u, h) for row in x])
         assert np.abs(got['irs_' + ear] - want).max() <= 1e-12 * np.abs(want).max()
         d = got['diffs_' + ear]
         assert np.array_equal(d, -d.T) and not d.diagonal().any()              # upsample_irs.m:31-32
         for i in range(n_rows):
             for j in range(i + 1, n_rows):
-                assert abs(d[i, j] - bb.delay_difference_cpu(x[i], x[j], u, h)) <= 1e-9
+                assert abs(d[i, j] - bank_oracle.delay_difference(x[i], x[j], u, h)) <= 1e-9
     # identical signals have zero delay difference; a pure delay of 3 samples reads as +3
     same = bb.upsample_irs(np.stack([left[0], left[0], np.roll(left[0], 3)]), np.stack([left[0]] * 3), u, filter=kind)
     assert abs(same['diffs_left'][0, 1]) <= 1e-9 and abs(same['diffs_left'][0, 2] - 3.0) <= 1e-3
