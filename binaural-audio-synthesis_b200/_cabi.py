@@ -85,6 +85,7 @@ def _load():
         'bas_plan_build': ([vp, vp, i, i, vp, vp, vp, i, ll, vp, vp, vp, vp], i),
         'bas_plan_build_host': ([vp, vp, i, i, vp, vp, vp, i, ll, vp, vp], i),
         'bas_ring_lookup_host': ([C.c_double, C.c_double, i, C.POINTER(i), dp, C.POINTER(i)], i),
+        'bas_plan_ring': ([vp, vp, i, i, vp, vp, ll, vp, vp, vp, vp], i),
         'bas_plan_ring_host': ([vp, vp, i, i, i, i, C.c_double, C.c_double, vp, vp, vp, vp], i),
         'bas_ir_synth': ([vp, i, i, vp, ll, i, vp, ll, vp], i),
         'bas_filter_row_pitch': ([i], i),

@@ -175,25 +175,37 @@ def delay_compensated_interpolation_with_delaydiff(irs_and_delaydiffs, before: i
     (2, K*U) when return_upsampled."""
     torch = _cabi.require_device()
     dev = _device_bank(irs_and_delaydiffs)
-    b, a = _grid_row(before), _grid_row(after)
     # (1 - alpha) is evaluated in alpha's own precision by the reference (apply_hrtf.py:90-91)
-    one_minus = float(1 - alpha)
-    terms = np.zeros((1, 2, _cabi.MAX_TERMS), dtype=_cabi.TERM_DTYPE)
-    delays = np.zeros(2, dtype=np.float64)
-    rc = lib.bas_plan_ring_host(dev.diffs_host[0].ctypes.data, dev.diffs_host[1].ctypes.data, dev.upsampling,
-                                dev.length, b, a, float(alpha), one_minus, terms.ctypes.data, delays.ctypes.data,
-                                None, None)
-    if rc < 0:
-        raise BasError(_cabi.last_error())
-    _raise_plan_error(rc)
+    terms_dev, delays_dev, status = _ring_plans(torch, dev, [(before, after, alpha)])
     width = dev.length if return_upsampled else dev.taps
-    terms_dev = torch.from_numpy(terms.view(np.uint8).reshape(-1)).to(dev.device)
     out = torch.empty((1, 2, width), dtype=torch.float32, device=dev.device)
     _cabi.check(lib.bas_ir_synth(dev.bank_pp.data_ptr(), dev.upsampling, dev.taps, terms_dev.data_ptr(), 1,
                                  _cabi.IR_UPSAMPLED if return_upsampled else _cabi.IR_PLANAR, out.data_ptr(), width,
                                  _stream(torch)), 'bas_ir_synth')
+    err = int(status.cpu()[0])
+    _raise_plan_error(err)
+    delays = delays_dev.cpu().numpy()
     irs = out[0].cpu().numpy().astype(np.float64)
-    return (delays[0], delays[1], irs)
+    return (delays[0, 0], delays[0, 1], irs)
+
+
+def _ring_plans(torch, dev, triples):
+    """bas_plan_ring for a list of (before, after, alpha): device tensors (terms, delays n x 2, status)."""
+    n = len(triples)
+    rows = np.empty((n, 2), dtype=np.int32)
+    weights = np.empty((n, 2), dtype=np.float64)
+    for i, (before, after, alpha) in enumerate(triples):
+        rows[i] = (_grid_row(before), _grid_row(after))
+        weights[i] = (float(alpha), float(1 - alpha))
+    rows_d = torch.from_numpy(rows).to(dev.device)
+    weights_d = torch.from_numpy(weights).to(dev.device)
+    terms = torch.empty(n * 2 * _cabi.MAX_TERMS * 8, dtype=torch.uint8, device=dev.device)
+    delays = torch.empty((n, 2), dtype=torch.float64, device=dev.device)
+    status = torch.empty(2, dtype=torch.int32, device=dev.device)
+    _cabi.check(lib.bas_plan_ring(dev.diffs[0].data_ptr(), dev.diffs[1].data_ptr(), dev.upsampling, dev.length, rows_d.data_ptr(),
+                                  weights_d.data_ptr(), n, terms.data_ptr(), delays.data_ptr(), status.data_ptr(), _stream(torch)),
+                'bas_plan_ring')
+    return terms, delays, status
 
 
 def delay_compensated_interpolation(irs_and_delaydiffs, before: int, after: int, alpha: float):
@@ -273,13 +285,10 @@ def interpolate_2d(irs_and_delaydiffs, elev, azim):
     torch = _cabi.require_device()
     dev = _device_bank(irs_and_delaydiffs)
     kind = sphere.az_kind(azim)
-    terms, trace = plan_points_host(irs_and_delaydiffs, [float(elev)], [float(azim)], kind)
-    _raise_plan_error(int(trace['err'][0]))
-    terms_dev = torch.from_numpy(terms.view(np.uint8).reshape(-1)).to(dev.device)
-    out = torch.empty((1, 2, dev.taps), dtype=torch.float32, device=dev.device)
-    _cabi.check(lib.bas_ir_synth(dev.bank_pp.data_ptr(), dev.upsampling, dev.taps, terms_dev.data_ptr(), 1,
-                                 _cabi.IR_PLANAR, out.data_ptr(), dev.taps, _stream(torch)), 'bas_ir_synth')
-    return out[0].cpu().numpy().astype(np.float64)
+    dirs = torch.tensor([float(elev), float(azim)], dtype=torch.float64).to(dev.device)
+    filt, status, _ = _plan_and_synth(torch, dev, dirs[0:1], dirs[1:2], kind, 1, _cabi.IR_PLANAR)
+    _raise_plan_error(int(status.cpu()[0]))
+    return filt[0].cpu().numpy().astype(np.float64)
 
 
 def interpolate_2d_deg(irs_and_delaydiffs, elev, azim):
@@ -755,8 +764,8 @@ def make_signal_move(in_signal, chunksize: int, index_function, irs_and_delaydif
     """apply_hrtf.py:294-353, the legacy 1-D renderer (superseded by make_signal_move_2d per its own
     docstring): index_function(t) gives a continuous index on the horizontal ring; every chunk is
     convolved with ONE ring-interpolated filter (delay_compensated_interpolation_easy, no cross-fade)
-    and overlap-added.  Same kernels as the 2-D path: the scalar part of the ring interpolation per
-    chunk on the host (bas_plan_ring_host), bas_ir_synth for the filters, and bas_render with
+    and overlap-added.  Same kernels as the 2-D path: the scalar part of the ring interpolation of all
+    chunks in one bas_plan_ring launch, bas_ir_synth for the filters, and bas_render with
     subchunksize = chunksize, for which every blend weight alpha_q is zero."""
     torch = _cabi.require_device()
     assert len(in_signal.shape) == 1, 'only mono signals for now'                   # apply_hrtf.py:308
@@ -767,23 +776,17 @@ def make_signal_move(in_signal, chunksize: int, index_function, irs_and_delaydif
     n_in = int(0.5 + np.ceil(n / chunksize) * chunksize)
     n_out = n_in + k - 1
     n_chunks = n_in // chunksize
-    terms = np.zeros((n_chunks + 1, 2, _cabi.MAX_TERMS), dtype=_cabi.TERM_DTYPE)
-    delays = np.zeros(2, dtype=np.float64)
+    triples = []
     for c in range(n_chunks):
         ci = index_function(c * chunksize)                                          # :334
         before, after = int(np.floor(ci)), int(np.ceil(ci))                         # :118-119
         alpha = ci - before
         if after == 97:
             after = 73                                                              # :121-122
-        rc = lib.bas_plan_ring_host(dev.diffs_host[0].ctypes.data, dev.diffs_host[1].ctypes.data, dev.upsampling, dev.length,
-                                    _grid_row(before), _grid_row(after), float(alpha), float(1 - alpha),
-                                    terms[c].ctypes.data, delays.ctypes.data, None, None)
-        if rc < 0:
-            raise BasError(_cabi.last_error())
-        _raise_plan_error(rc, ' (chunk %d)' % c)
-    terms[n_chunks] = terms[n_chunks - 1]         # the boundary after the last chunk: present in the layout, weight 0
+        triples.append((before, after, alpha))
+    triples.append(triples[-1])                   # the boundary after the last chunk: present in the layout, weight 0
+    terms_dev, _, status = _ring_plans(torch, dev, triples)
     stream = _stream(torch)
-    terms_dev = torch.from_numpy(terms.view(np.uint8).reshape(-1)).to(device)
     filt = torch.empty((n_chunks + 1, lib.bas_filter_row_pitch(k), 2), dtype=torch.float32, device=device)
     _cabi.check(lib.bas_ir_synth(dev.bank_pp.data_ptr(), dev.upsampling, k, terms_dev.data_ptr(), n_chunks + 1, _cabi.IR_ROWS,
                                  filt.data_ptr(), k, stream), 'bas_ir_synth')
@@ -796,6 +799,9 @@ def make_signal_move(in_signal, chunksize: int, index_function, irs_and_delaydif
     _cabi.check(lib.bas_render(x.data_ptr(), n_in, n_in, 1, n_in, chunksize, chunksize, k, filt.data_ptr(), None, 0, n_out,
                                out.data_ptr(), stride, 0, peak.data_ptr(), variant, None, 0, stream), 'bas_render')
     _cabi.check(lib.bas_normalise(out.data_ptr(), 2 * stride, peak.data_ptr(), stream), 'bas_normalise')   # :349-351
+    err, where = (int(v) for v in status.cpu())
+    if err:
+        _raise_plan_error(err, ' (chunk %d)' % where)
     if PROGRESS:
         print(' 100.0%      ')                                                      # :346
     return out[:, :n_out].cpu().numpy().T

@@ -202,6 +202,52 @@ extern "C" int bas_ring_lookup_host(double ring_elev, double azim, int az_kind, 
     return 0;
 }
 
+// Ring plans on the device: one thread per (item, ear), same bas_plan_ring_ear as the host twin below.
+// rows: {before, after} per item; weights: {alpha, 1 - alpha} per item (the caller evaluates 1 - alpha in
+// alpha's own precision, apply_hrtf.py:90); delays: the two values the reference returns (:106).
+__global__ void __launch_bounds__(64)
+bas_plan_ring_kernel(const double* __restrict__ diffs_l, const double* __restrict__ diffs_r, int U, long long L,
+                     const int* __restrict__ rows, const double* __restrict__ weights, long long n,
+                     BasTerm* __restrict__ terms, double* __restrict__ delays, int* __restrict__ status) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = t >> 1;
+    const int ear = (int)(t & 1);
+    if (i >= n) return;
+    BasTerm local[BAS_MAX_TERMS];
+    long long lo[2], hi[2];
+    double d = 0.0;
+    const int err = bas_plan_ring_ear(ear ? diffs_r : diffs_l, U, L, rows[2 * i], rows[2 * i + 1], weights[2 * i], weights[2 * i + 1],
+                                      local, &d, lo, hi);
+    int4* dst = reinterpret_cast<int4*>(terms + (i * 2 + ear) * BAS_MAX_TERMS);
+#pragma unroll
+    for (int k = 0; k < BAS_MAX_TERMS / 2; ++k)
+        dst[k] = make_int4(local[2 * k].row_shift, __float_as_int(local[2 * k].weight),
+                           local[2 * k + 1].row_shift, __float_as_int(local[2 * k + 1].weight));
+    delays[2 * i + ear] = d;
+    if (err && status) {
+        atomicOr(status, err);
+        atomicMin(status + 1, (int)(i > INT_MAX ? INT_MAX : i));
+    }
+}
+
+extern "C" int bas_plan_ring(const double* diffs_left_dev, const double* diffs_right_dev, int U, int L, const int* rows_dev,
+                             const double* weights_dev, long long n, bas_term* terms_dev, double* delays_dev, int* status_dev,
+                             void* stream) {
+    BAS_CHECK_ARG(diffs_left_dev && diffs_right_dev && rows_dev && weights_dev && terms_dev && delays_dev, "null pointer");
+    BAS_CHECK_ARG(U >= 1 && L >= U && L % U == 0 && L < (1 << 20), "need 1 <= U, U | L, L < 2^20");
+    BAS_CHECK_ARG(n >= 0 && n < 0x3fffffffLL, "n");
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (status_dev) {
+        BAS_CUDA(cudaMemsetAsync(status_dev, 0, sizeof(int), st));
+        BAS_CUDA(cudaMemsetAsync(status_dev + 1, 0x7f, sizeof(int), st));
+    }
+    bas_plan_ring_kernel<<<(unsigned)bas_ceil_div(2 * n, 64), 64, 0, st>>>(diffs_left_dev, diffs_right_dev, U, (long long)L, rows_dev, weights_dev,
+                                                                         n, reinterpret_cast<BasTerm*>(terms_dev), delays_dev, status_dev);
+    BAS_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int bas_plan_ring_host(const double* diffs_left, const double* diffs_right, int U, int L, int before,
                                   int after, double alpha, double one_minus_alpha, bas_term* terms,
                                   double* delays, int64_t* lo, int64_t* hi) {

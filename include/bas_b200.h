@@ -103,7 +103,17 @@ int bas_plan_build_host(const double* diffs_left, const double* diffs_right, int
  * raises ValueError, sphere.py:100-101), BAS_ERR_AZIM_ASSERT if the azimuth assertion fails. */
 int bas_ring_lookup_host(double ring_elev, double azim, int az_kind, int* before, double* alpha, int* after);
 
-/* delay_compensated_interpolation_with_delaydiff, apply_hrtf.py:53-106, scalar part for both ears.
+/* delay_compensated_interpolation_with_delaydiff, apply_hrtf.py:53-106, scalar part on the device for n
+ * (before, after, alpha) triples: rows_dev {before, after} x n (grid rows, 0..186), weights_dev
+ * {alpha, 1 - alpha} x n (1 - alpha evaluated by the caller in alpha's own precision, :90),
+ * terms_dev n x 2 x BAS_MAX_TERMS, delays_dev n x 2 (the returned delays, :106), status_dev as in
+ * bas_plan_build.  Used by the ring entry points and by the legacy renderer make_signal_move (:334). */
+int bas_plan_ring(const double* diffs_left_dev, const double* diffs_right_dev, int U, int L, const int* rows_dev,
+                  const double* weights_dev, long long n, bas_term* terms_dev, double* delays_dev, int* status_dev,
+                  void* stream);
+
+/* delay_compensated_interpolation_with_delaydiff, apply_hrtf.py:53-106, scalar part for both ears (host
+ * twin of bas_plan_ring, same source; CPU-side index-parity tests).
  * one_minus_alpha is passed separately because the reference evaluates it in the dtype of alpha.
  * terms: 2 x BAS_MAX_TERMS (host).  delays: the two returned delays (apply_hrtf.py:106).
  * lo/hi: per ear floor/ceil of {-d, alpha*d} (may be NULL). */
