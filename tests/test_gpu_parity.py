@@ -393,3 +393,42 @@ def test_signal_that_is_not_whole_rows_takes_the_bulk_copy_path(bas, synth_bank)
         outs.append((out.cpu().numpy(), float(peak)))
     assert np.array_equal(outs[0][0], outs[1][0]) and outs[0][1] == outs[1][1]
     assert np.abs(outs[0][0]).max() > 0
+
+
+@pytest.mark.parametrize('seed', range(20))
+def test_randomised_geometries_vs_oracle(bas, oracle, seed):
+    """Seeded random (K, C, S, N, trajectory) draws: taps that are not multiples of 32 or 4, chunks of a
+    single subchunk, subchunk sizes the tiled kernel does not take (generic kernel), signals shorter than
+    a chunk, trajectories that wrap the azimuth and leave the elevation range (clamped rings, pole)."""
+    rng = np.random.default_rng(1000 + seed)
+    k_taps = int(rng.choice([1, 3, 17, 32, 33, 64, 100, 127, 256, 300]))
+    s = int(rng.choice([32, 32, 32, 16, 64, 8]))
+    c = s * int(rng.choice([1, 2, 4, 16]))
+    n = int(rng.integers(1, 6000))
+    f = _bank_fields(bas)
+    bank = GoldenBankLocal(8, f['diffs_left'], f['diffs_right'], f['irs_left'][:, :k_taps * 8], f['irs_right'][:, :k_taps * 8])
+    x = (0.05 * rng.standard_normal(n)).astype(np.float32)
+    if seed % 5 == 0:
+        x *= 40.0                                               # peak above 1: the division of apply_hrtf.py:462-464
+    a0, a1, e0, e1 = rng.uniform(-8, 8), rng.uniform(-0.02, 0.02), rng.uniform(-2, 2), rng.uniform(-0.001, 0.001)
+    kind = (float, np.float64, np.float32)[seed % 3]
+    traj = lambda t: (e0 + e1 * t, kind((a0 + a1 * t) % (2 * np.pi)))
+    want = oracle.make_signal_move_2d(x, c, s, traj, bank)
+    got = bas.make_signal_move_2d(x, c, s, traj, bank)
+    close(got, want)
+
+
+_BANK_FIELDS = {}
+
+
+def _bank_fields(bas):
+    if 'f' not in _BANK_FIELDS:
+        _BANK_FIELDS['f'] = bas.bank_synth.build_bank(8, seed=0)
+    return _BANK_FIELDS['f']
+
+
+class GoldenBankLocal:
+    def __init__(self, upsampling, diffs_left, diffs_right, irs_left, irs_right):
+        self.upsampling = int(upsampling)
+        self.diffs_left, self.diffs_right = np.asarray(diffs_left, dtype=np.float64), np.asarray(diffs_right, dtype=np.float64)
+        self.irs_left, self.irs_right = np.asarray(irs_left, dtype=np.float64), np.asarray(irs_right, dtype=np.float64)
