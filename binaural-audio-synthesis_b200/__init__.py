@@ -12,6 +12,7 @@ from .apply_hrtf import (                                                  # noq
     delay_compensated_interpolation_with_delaydiff,
     delay_compensated_interpolation,
     delay_compensated_interpolation_easy,
+    delay_signal_float,
     interpolate_2d,
     interpolate_2d_deg,
     interpolate_2d_batch,
@@ -25,7 +26,7 @@ from .apply_hrtf import (                                                  # noq
 
 __all__ = [
     'load_irs_and_delaydiffs', 'delay_compensated_interpolation_with_delaydiff',
-    'delay_compensated_interpolation', 'delay_compensated_interpolation_easy', 'interpolate_2d',
+    'delay_compensated_interpolation', 'delay_compensated_interpolation_easy', 'delay_signal_float', 'interpolate_2d',
     'interpolate_2d_deg', 'interpolate_2d_batch', 'make_signal_move_2d', 'make_signal_move', 'render_sources',
     'render_geometry', 'evaluate_trajectory', 'plan_points_host', 'sphere', 'bank_synth', 'bank_builder', 'distributed',
     'BasError',

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libbas_b200.so')
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 N_DIRECTIONS = 187
 MAX_TERMS = 16
 AZ_PYFLOAT, AZ_F64, AZ_F32 = 0, 1, 2
@@ -87,6 +87,7 @@ def _load():
         'bas_ring_lookup_host': ([C.c_double, C.c_double, i, C.POINTER(i), dp, C.POINTER(i)], i),
         'bas_plan_ring': ([vp, vp, i, i, vp, vp, ll, vp, vp, vp, vp], i),
         'bas_plan_ring_host': ([vp, vp, i, i, i, i, C.c_double, C.c_double, vp, vp, vp, vp], i),
+        'bas_delay_signal_float': ([vp, ll, ll, ll, C.c_double, i, vp, vp], i),
         'bas_ir_synth': ([vp, i, i, vp, ll, i, vp, ll, vp], i),
         'bas_filter_row_pitch': ([i], i),
         'bas_render': ([vp, ll, ll, i, ll, i, i, i, vp, vp, ll, ll, vp, ll, i, vp, i, vp, ll, vp], i),
@@ -94,14 +95,13 @@ def _load():
         'bas_normalise': ([vp, ll, vp, vp], i),
         'bas_peak': ([vp, ll, vp, vp], i),
         'bas_copy_2d': ([vp, ll, vp, ll, ll, ll, i, vp], i),
+        'bas_host_register': ([vp, ll], i),
+        'bas_host_unregister': ([vp], i),
         'bas_pipeline_arena_bytes': ([i, ll, i, i, i, ll, i, C.POINTER(ll)], ll),
         'bas_pipeline_upload': ([C.POINTER(PipelineJob), i, C.POINTER(ll)], i),
         'bas_pipeline_phase': ([C.POINTER(PipelineJob), i, i, ll, ll, ll, ll], i),
         'bas_pipeline_trace': ([i, C.c_char_p, C.c_size_t], i),
         'bas_memset': ([vp, i, ll, vp], i),
-        'bas_probe_clock': ([i, i, i, i, vp, vp, vp], i),
-        'bas_probe_block': ([i, i, i, vp, vp], i),
-        'bas_probe_fma': ([i, i, i, i, vp, vp], i),
     }
     for name, (argtypes, restype) in sigs.items():
         fn = getattr(lib, name)          # AttributeError here = header and library out of step
@@ -119,6 +119,15 @@ def last_error() -> str:
     buf = C.create_string_buffer(512)
     lib.bas_last_error(buf, 512)
     return buf.value.decode(errors='replace')
+
+
+def decode_status(words):
+    """(error bits of the earliest failing point, its index) from the two status words of a plan
+    launch (include/bas_b200.h): the reference raises at the first bad trajectory point."""
+    if not int(words[0]):
+        return 0, 0
+    packed = int(words[1])
+    return packed & 7, packed >> 3
 
 
 def check(rc: int, what: str) -> None:

@@ -20,8 +20,8 @@ CPU path: without a CUDA device every compute call raises.
 from __future__ import annotations
 
 import ctypes as C
-import math
 import threading
+import weakref
 
 import numpy as np
 
@@ -76,11 +76,24 @@ def _device_bank(bank) -> _BankDevice:
             setattr(bank, '_bas_device', cache)
         except (AttributeError, TypeError):
             pass
+    mark = _bank_fingerprint(bank)
     state = cache.get(device.index)
-    if state is None:
-        state = _BankDevice(bank, torch, device)
+    if state is None or state.fingerprint != mark:
+        state = _BankDevice(bank, torch, device)          # first use, or the caller changed the bank's arrays
+        state.fingerprint = mark
         cache[device.index] = state
     return state
+
+
+def _bank_fingerprint(bank):
+    """Cheap identity of a bank's contents: array identities, shapes and a strided sample of every
+    array (a few hundred values), so that the cached device copy is dropped when the caller rebinds
+    or overwrites the arrays.  Costs microseconds; not a cryptographic guarantee."""
+    parts = [int(bank.upsampling)]
+    for name in ('irs_left', 'irs_right', 'diffs_left', 'diffs_right'):
+        a = np.asarray(getattr(bank, name))
+        parts += [a.shape, a.__array_interface__['data'][0], float(a[::17, ::61].sum()) if a.ndim == 2 else float(a.sum())]
+    return tuple(parts)
 
 
 def load_irs_and_delaydiffs(filename='irs_and_delaydiffs_compensated_6.mat', samples_to_keep=512):
@@ -116,6 +129,11 @@ def _stream(torch):
 
 
 def _raise_plan_error(err: int, where: str = ''):
+    """Raise what the reference raises for the error bits of ONE trajectory point (the earliest failing
+    one, _cabi.decode_status), in the order the reference reaches its checks: the azimuth assertion of
+    the ring lookups (sphere.py:87, called at apply_hrtf.py:214) comes before the vertical weight
+    (:266) and before any int(floor(nan)) (:149).  Unlike the reference, which raises in the middle of
+    its chunk loop, the exception surfaces after the device work of the call has been enqueued."""
     if err & _cabi.ERR_AZIM_ASSERT:
         raise AssertionError('azim >= 0' + where)                                      # sphere.py:87
     if err & _cabi.ERR_VERT_ASSERT:
@@ -182,8 +200,7 @@ def delay_compensated_interpolation_with_delaydiff(irs_and_delaydiffs, before: i
     _cabi.check(lib.bas_ir_synth(dev.bank_pp.data_ptr(), dev.upsampling, dev.taps, terms_dev.data_ptr(), 1,
                                  _cabi.IR_UPSAMPLED if return_upsampled else _cabi.IR_PLANAR, out.data_ptr(), width,
                                  _stream(torch)), 'bas_ir_synth')
-    err = int(status.cpu()[0])
-    _raise_plan_error(err)
+    _raise_plan_error(_cabi.decode_status(status.cpu())[0])
     delays = delays_dev.cpu().numpy()
     irs = out[0].cpu().numpy().astype(np.float64)
     return (delays[0, 0], delays[0, 1], irs)
@@ -223,6 +240,31 @@ def delay_compensated_interpolation_easy(irs_and_delaydiffs, continuous_index: f
     return delay_compensated_interpolation(irs_and_delaydiffs, before, after, alpha)
 
 
+def delay_signal_float(in_sig, samples: float, downsample=1):
+    """apply_hrtf.py:127-165: delay `in_sig` circularly by a non-integer number of samples (linear
+    interpolation between the two neighbouring integer delays, np.roll semantics), then keep every
+    `downsample`-th sample.  float64 in, float64 out, bit-identical to the reference (the blend runs
+    in IEEE double on the device without fused multiply-adds).  Inside interpolate_2d the same
+    operation is fused into bas_ir_synth; this entry point exists for callers that import it."""
+    torch = _cabi.require_device()
+    before = int(np.floor(samples))                                 # :149
+    after = int(np.ceil(samples))                                   # :150
+    a = samples - before                                            # :151
+    x = np.ascontiguousarray(in_sig, dtype=np.float64)
+    if x.ndim != 1:
+        raise ValueError('delay_signal_float takes a 1-D signal')
+    n = x.size
+    d = int(downsample) if downsample > 1 else 1                    # :160
+    if n == 0:
+        return np.zeros(0, dtype=np.float64)
+    device = torch.device('cuda', torch.cuda.current_device())
+    x_d = torch.from_numpy(x).to(device)
+    out = torch.empty((n + d - 1) // d, dtype=torch.float64, device=device)
+    _cabi.check(lib.bas_delay_signal_float(x_d.data_ptr(), n, before, after, float(a), d, out.data_ptr(), _stream(torch)),
+                'bas_delay_signal_float')
+    return out.cpu().numpy()
+
+
 # --------------------------------------------------------------------------------------------------
 # 2-D interpolation (apply_hrtf.py:167-281)
 # --------------------------------------------------------------------------------------------------
@@ -242,7 +284,7 @@ def interpolate_2d_batch(irs_and_delaydiffs, elev, azim, az_kind=_cabi.AZ_F64, r
         raise ValueError('elev and azim must have the same number of points')
     filt, status, trace = _plan_and_synth(torch, dev, elev_d, azim_d, az_kind, n, _cabi.IR_PLANAR, return_trace)
     if check:
-        err, where = (int(v) for v in status.cpu())
+        err, where = _cabi.decode_status(status.cpu())
         if err:
             _raise_plan_error(err, ' (direction %d)' % where)
     if return_trace:
@@ -287,7 +329,7 @@ def interpolate_2d(irs_and_delaydiffs, elev, azim):
     kind = sphere.az_kind(azim)
     dirs = torch.tensor([float(elev), float(azim)], dtype=torch.float64).to(dev.device)
     filt, status, _ = _plan_and_synth(torch, dev, dirs[0:1], dirs[1:2], kind, 1, _cabi.IR_PLANAR)
-    _raise_plan_error(int(status.cpu()[0]))
+    _raise_plan_error(_cabi.decode_status(status.cpu())[0])
     return filt[0].cpu().numpy().astype(np.float64)
 
 
@@ -310,30 +352,84 @@ def render_geometry(n_samples: int, chunksize: int, subchunksize: int, irs_and_d
     return ir_length, in_length, out_length
 
 
-def evaluate_trajectory(elev_azim_function, times):
-    """Directions at the chunk boundaries.  The reference calls elev_azim_function(t) with a Python
-    int for t = 0, C, ..., N_in (apply_hrtf.py:429, :435).  A callable that sets
-    `vectorized = True` is called once with the whole int64 array instead and must return two
-    arrays; its azimuths are treated as float64 scalars unless it also sets `az_kind`.
-    Returns (elev float64[n], azim float64[n], kinds uint8[n] or a single kind)."""
-    if getattr(elev_azim_function, 'vectorized', False):
+# Trajectories.  The reference calls elev_azim_function(t) once per chunk boundary with a Python int
+# (apply_hrtf.py:429, :435): 5,169 Python calls for a 60 s source, 24 ms - forty times the rest of the
+# call.  Most trajectories are arithmetic on t that works unchanged on an array (every lambda in the
+# reference's main does, apply_hrtf.py:583-593), so a plain callable is TRIAL-VECTORISED: one scalar
+# call fixes the scalar type of the azimuth (it selects the arithmetic of the ring lookup, SURVEY.md
+# section 5), one call with the whole int64 array of boundaries follows, and the array result is
+# accepted only if it equals scalar calls at TRAJECTORY_CHECKS spot-check boundaries bit for bit
+# (values and scalar kinds).  Anything else - an exception, a wrong shape, a mismatch - falls back to
+# the reference's loop.  A callable can opt out (`fn.vectorized = False`) or declare itself array-safe
+# and skip the checks (`fn.vectorized = True`, optionally `fn.az_kind`).
+TRAJECTORY_TRIAL_MIN = 24        # fewer boundaries than this: just loop
+TRAJECTORY_CHECKS = 16           # scalar spot checks of the first array evaluation of a callable
+TRAJECTORY_RECHECKS = 3          # spot checks of later evaluations (later phases of the same call)
+
+
+def _scalar_point(elev_azim_function, t):
+    e, a = elev_azim_function(int(t))                # a Python int, like range() gives the reference
+    return float(e), float(a), sphere.az_kind(a)
+
+
+def _try_vectorized(elev_azim_function, times, n_checks, rng):
+    """(elev, azim, kind) from one array call, or None if the callable cannot be trusted with arrays."""
+    n = len(times)
+    try:
+        e0, a0, kind = _scalar_point(elev_azim_function, times[0])
+        res = elev_azim_function(np.asarray(times, dtype=np.int64))
+        if not isinstance(res, tuple) or len(res) != 2:
+            return None
+        elev = np.asarray(res[0])
+        azim = np.asarray(res[1])
+        if elev.dtype.kind not in 'fiu' or azim.dtype.kind not in 'fiu' or elev.ndim > 1 or azim.ndim > 1:
+            return None
+        # an array azimuth behaves like its scalars: float32 arrays -> np.float32 scalars, everything else
+        # -> the kind the scalar call showed (Python float and np.float64 compute the same float64 values)
+        if (azim.dtype == np.float32) != (kind == _cabi.AZ_F32):
+            return None
+        elev = np.ascontiguousarray(np.broadcast_to(elev.astype(np.float64), (n,)))
+        azim = np.ascontiguousarray(np.broadcast_to(azim.astype(np.float64), (n,)))
+        picks = [0, n - 1] + [int(i) for i in rng.integers(0, n, max(0, n_checks - 2))]
+        for i in picks:
+            e, a, kd = (e0, a0, kind) if i == 0 else _scalar_point(elev_azim_function, times[i])
+            same = (e == elev[i] or (e != e and elev[i] != elev[i])) and (a == azim[i] or (a != a and azim[i] != azim[i]))
+            if not same or kd != kind:
+                return None
+        return elev, azim, int(kind)
+    except Exception:
+        return None
+
+
+def evaluate_trajectory(elev_azim_function, times, state=None):
+    """Directions at the chunk boundaries `times` (t = 0, C, ..., N_in; apply_hrtf.py:429, :435).
+    Returns (elev float64[n], azim float64[n], kinds uint8[n] or a single kind).  `state` (a dict)
+    carries the outcome of the trial vectorisation between the phases of one call."""
+    n = len(times)
+    declared = getattr(elev_azim_function, 'vectorized', None)
+    if declared is True:
         elev, azim = elev_azim_function(np.asarray(times, dtype=np.int64))
         azim = np.asarray(azim)
         kind = getattr(elev_azim_function, 'az_kind', None)
         if kind is None:
             kind = _cabi.AZ_F32 if azim.dtype == np.float32 else _cabi.AZ_F64
-        elev = np.broadcast_to(np.asarray(elev, dtype=np.float64), (len(times),))
-        azim = np.broadcast_to(azim.astype(np.float64), (len(times),))
+        elev = np.broadcast_to(np.asarray(elev, dtype=np.float64), (n,))
+        azim = np.broadcast_to(azim.astype(np.float64), (n,))
         return np.ascontiguousarray(elev), np.ascontiguousarray(azim), int(kind)
-    n = len(times)
+    state = {} if state is None else state
+    if declared is None and n >= TRAJECTORY_TRIAL_MIN and state.get('mode') != 'loop':
+        first = 'mode' not in state
+        rng = state.setdefault('rng', np.random.default_rng(n))
+        res = _try_vectorized(elev_azim_function, times, TRAJECTORY_CHECKS if first else TRAJECTORY_RECHECKS, rng)
+        if res is not None and (first or res[2] == state.get('kind')):
+            state['mode'], state['kind'] = 'array', res[2]
+            return res
+        state['mode'] = 'loop'
     elev = np.empty(n, dtype=np.float64)
     azim = np.empty(n, dtype=np.float64)
     kinds = np.empty(n, dtype=np.uint8)
     for i, t in enumerate(times):
-        e, a = elev_azim_function(int(t))            # a Python int, like range() gives the reference
-        elev[i] = e
-        azim[i] = a
-        kinds[i] = sphere.az_kind(a)
+        elev[i], azim[i], kinds[i] = _scalar_point(elev_azim_function, t)
     if n and (kinds == kinds[0]).all():
         return elev, azim, int(kinds[0])
     return elev, azim, kinds
@@ -346,6 +442,16 @@ PIPELINE_MAX_SEGMENTS = 64
 _SEGMENT_ALIGN = 8192            # output samples; a whole number of render tiles for every tile width
 
 _side_streams = {}
+POISON_SCRATCH = False           # tests: fill freshly allocated device scratch with NaN, so that any read of an
+                                 # uninitialised sample shows up in the output instead of depending on allocator history
+
+
+def _scratch(torch, shape, dtype, device):
+    t = torch.empty(shape, dtype=dtype, device=device)
+    if POISON_SCRATCH:
+        t.view(torch.uint8).fill_(0xff)
+    return t
+
 MIX_GROUP_SOURCES = 16           # mixing more sources than this: groups, planned / synthesised while the previous group renders
 
 
@@ -398,6 +504,51 @@ def _directions(elev_azim_functions, n_src: int, n_in: int, chunksize: int):
     return elev, azim, kinds
 
 
+# Pageable input arrays.  The reference's caller passes an ordinary ndarray (apply_hrtf.py:633); a
+# DMA engine can only read page-locked memory, and a staged copy of a 60 s signal costs more than the
+# rest of the call.  A large float32 array that owns its buffer is therefore page-locked IN PLACE on
+# first sight (cudaHostRegister, about the cost of one staged copy) and stays registered for as long as
+# the array object lives: a weakref finaliser releases it when the array dies, so repeated calls on the
+# same signal upload by direct DMA.  Arrays that do not qualify take the driver's staged copy.
+REGISTER_MIN_BYTES = 1 << 20
+REGISTER_MAX_ARRAYS = 16
+_registered = {}                 # id(owner) -> (address, bytes, finaliser), oldest first
+_registered_lock = threading.Lock()
+
+
+def _release_registration(key, address):
+    with _registered_lock:
+        _registered.pop(key, None)
+    lib.bas_host_unregister(address)
+
+
+def _pin_in_place(arr) -> bool:
+    """Page-lock the buffer behind numpy array `arr` (see above); True if it is registered now."""
+    owner = arr
+    while isinstance(owner.base, np.ndarray):
+        owner = owner.base
+    if owner.base is not None or not owner.flags.owndata or owner.nbytes < REGISTER_MIN_BYTES:
+        return False
+    key, address, nbytes = id(owner), owner.ctypes.data, owner.nbytes
+    with _registered_lock:
+        hit = _registered.get(key)
+        if hit is not None and hit[0] == address and hit[1] == nbytes:
+            return True
+        stale = [hit[2]] if hit is not None else []                  # the array was resized in place
+        while len(_registered) - len(stale) >= REGISTER_MAX_ARRAYS:
+            oldest = next(k for k in _registered if k != key)
+            stale.append(_registered.pop(oldest)[2])
+    for fin in stale:
+        fin()                                                        # runs _release_registration now
+    if lib.bas_host_register(address, nbytes) != 0:
+        return False
+    fin = weakref.finalize(owner, _release_registration, key, address)
+    fin.atexit = False                                               # the CUDA runtime may be gone by then
+    with _registered_lock:
+        _registered[key] = (address, nbytes, fin)
+    return True
+
+
 class _HostCache(threading.local):
     """Per-thread, per-device scratch of the host pipeline, grown on demand and reused between calls
     (every call ends with its device work complete, so nothing is in flight when they are reused)."""
@@ -412,6 +563,8 @@ class _HostCache(threading.local):
             self.arena[device.index] = None
             a = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
             self.arena[device.index] = a
+        if POISON_SCRATCH:
+            a.fill_(0xff)
         return a
 
     def pinned_bytes(self, torch, name, nbytes):
@@ -504,12 +657,13 @@ def _render_pipeline(torch, dev, src, chunksize, subchunksize, elev_azim_functio
     elif len(elev_azim_functions) != n_src:
         raise ValueError('need one trajectory per source')
     kinds_ptr = staged.data_ptr() + n_dirs * 16
+    traj_state = [{} for _ in range(n_src)]
     for i, (pa, pb, pt0, pt1) in enumerate(phases):
         # the trajectory of this phase is evaluated while the signal and the earlier phases travel
         if pre is None and pt1 > pt0:
             times = np.arange(pt0 * chunksize, (pt1 - 1) * chunksize + 1, chunksize, dtype=np.int64)
             for s, fn in enumerate(elev_azim_functions):
-                e, a, kd = evaluate_trajectory(fn, times)
+                e, a, kd = evaluate_trajectory(fn, times, traj_state[s])
                 elev_h[s, pt0:pt1] = e
                 azim_h[s, pt0:pt1] = a
                 kinds_h[s, pt0:pt1] = kd
@@ -520,7 +674,7 @@ def _render_pipeline(torch, dev, src, chunksize, subchunksize, elev_azim_functio
         job.az_kind_host = None if uniform else kinds_ptr
         _cabi.check(lib.bas_pipeline_phase(C.byref(job), i, len(phases), pt0, pt1, pa, pb), 'bas_pipeline_phase')
     words = small.numpy()[:4 * (2 + n_src)].view(np.int32)
-    err, where = int(words[0]), int(words[1])
+    err, where = _cabi.decode_status(words)
     if err:
         _raise_plan_error(err, ' (trajectory point %d of source %d)' % (where % n_pts, where // n_pts))
     peaks_host = words[2:].view(np.float32).copy()
@@ -569,9 +723,13 @@ def render_sources(signals, chunksize: int, subchunksize: int, elev_azim_functio
     main = torch.cuda.current_stream()
     stream = main.cuda_stream
     if isinstance(signals, torch.Tensor):
-        src = signals
+        # CUDA tensors are used where they lie; host tensors are converted like host arrays
+        src = signals if signals.is_cuda else signals.detach().to(torch.float32).contiguous()
     else:
-        src = torch.from_numpy(np.ascontiguousarray(signals, dtype=np.float32))
+        host = np.ascontiguousarray(signals, dtype=np.float32)
+        if not return_device:
+            _pin_in_place(host)
+        src = torch.from_numpy(host)
     if src.dim() != 2:
         raise ValueError('signals must be (n_src, N)')
     n_src, n = src.shape
@@ -582,6 +740,14 @@ def render_sources(signals, chunksize: int, subchunksize: int, elev_azim_functio
         raise ValueError('time_range outside [0, %d]' % n_out)
     count = p1 - p0
     n_pts = n_in // chunksize + 1
+    if n == 0:
+        # An empty signal: the reference still evaluates the trajectory at t = 0 and interpolates that
+        # filter (apply_hrtf.py:429, with its assertions), runs no chunk, and returns K - 1 zero pairs.
+        elev, azim, kinds = _directions(elev_azim_functions, n_src, 0, chunksize)
+        interpolate_2d_batch(irs_and_delaydiffs, elev, azim, kinds)
+        zeros = torch.zeros((2, count) if mix else (n_src, 2, count), dtype=torch.float32, device=device if return_device else 'cpu')
+        result = zeros if return_device else zeros.numpy()
+        return (result, np.zeros(n_src, dtype=np.float32)) if return_peaks else result
     if not src.is_cuda and not return_device and src.dtype == torch.float32 and _host_directions(elev_azim_functions):
         return _render_pipeline(torch, dev, src, chunksize, subchunksize, elev_azim_functions, mix, normalise, variant,
                                 p0, p1, return_peaks)
@@ -595,13 +761,16 @@ def render_sources(signals, chunksize: int, subchunksize: int, elev_azim_functio
     if resident:
         x = src
     else:
-        x = torch.empty((n_src, n_in), dtype=torch.float32, device=device)
+        x = _scratch(torch, (n_src, n_in), torch.float32, device)
         if n_in > n:
             x[:, n:].zero_()
         if src.is_cuda:
             x[:, :n].copy_(src)
         elif count > 0:
-            lo = max(0, p0 - (k - 1)) // 4 * 4              # first and last input sample any output needs
+            # first input sample the kernels READ (the tiled kernel multiplies samples back to
+            # p0/32*32 - 32*ceil(K/32) by zero-padding taps: they must be initialised, 0 * NaN = NaN) and
+            # one past the last sample any output needs
+            lo = max(0, p0 // 32 * 32 - 32 * ((k + 31) // 32))
             hi = min(n, p1)
             up.wait_stream(main)                            # x was just allocated on `main`
             _cabi.check(lib.bas_copy_2d(x.data_ptr() + 4 * lo, 4 * n_in, src.data_ptr() + 4 * lo, 4 * n, 4 * (hi - lo), n_src, 1,
@@ -717,12 +886,13 @@ def render_sources(signals, chunksize: int, subchunksize: int, elev_azim_functio
         main.synchronize()
 
     host = small.numpy()
-    err, where = int(host[0]), int(host[1])
+    err, where = _cabi.decode_status(host)
     if grouped:                                  # one status pair per source group: first failing direction overall
         per_group = status_all.cpu().numpy()
-        for gi in np.nonzero(per_group[:, 0])[0]:
-            err |= int(per_group[gi, 0])
-            where = min(where if where else 0x7f7f7f7f, int(per_group[gi, 1]) + int(gi) * MIX_GROUP_SOURCES * n_pts)
+        failing = np.nonzero(per_group[:, 0])[0]
+        if failing.size:
+            err, where = _cabi.decode_status(per_group[failing[0]])
+            where += int(failing[0]) * MIX_GROUP_SOURCES * n_pts
     if err:
         _raise_plan_error(err, ' (trajectory point %d of source %d)' % (where % n_pts, where // n_pts))
     peaks_host = host[2:].view(np.float32).copy()
@@ -799,7 +969,7 @@ def make_signal_move(in_signal, chunksize: int, index_function, irs_and_delaydif
     _cabi.check(lib.bas_render(x.data_ptr(), n_in, n_in, 1, n_in, chunksize, chunksize, k, filt.data_ptr(), None, 0, n_out,
                                out.data_ptr(), stride, 0, peak.data_ptr(), variant, None, 0, stream), 'bas_render')
     _cabi.check(lib.bas_normalise(out.data_ptr(), 2 * stride, peak.data_ptr(), stream), 'bas_normalise')   # :349-351
-    err, where = (int(v) for v in status.cpu())
+    err, where = _cabi.decode_status(status.cpu())
     if err:
         _raise_plan_error(err, ' (chunk %d)' % where)
     if PROGRESS:

@@ -16,7 +16,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from . import sphere
+from . import _grid
 
 BASE_LENGTH = 512   # samples per measured HRIR (upsample_irs.m:37-38)
 
@@ -27,7 +27,7 @@ def synthetic_hrirs(seed: int = 0, length: int = BASE_LENGTH):
     low-passed noise tail.  Neighbouring grid cells differ by at most a few samples of
     delay, like real HRIRs, so the delay-compensated interpolation is exercised properly."""
     rng = np.random.default_rng(seed)
-    tab = sphere.index_elev_azim.astype(np.float64)
+    tab = _grid.get_index_elev_azim().astype(np.float64)
     elev, azim = tab[:, 1], tab[:, 2]
     n = np.arange(length, dtype=np.float64)
     lateral = np.sin(azim) * np.cos(elev)          # +1: source fully to the left

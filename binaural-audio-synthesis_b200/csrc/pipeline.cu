@@ -127,8 +127,11 @@ extern "C" int bas_pipeline_upload(const bas_pipeline_job* j, int n_phases, cons
     mark("upload begins", 0, 0, up);
     if (j->n_in > j->n)
         BAS_CUDA(cudaMemset2DAsync(x + j->n, (size_t)j->n_in * 4, 0, (size_t)(j->n_in - j->n) * 4, (size_t)j->n_src, up));
-    long long lo = j->p_begin - (j->K - 1);
-    lo = lo < 0 ? 0 : lo;                                     // first input sample any output needs
+    // First input sample the render kernels READ: the tiled kernel works on whole 32-sample rows and on
+    // ceil(K/32) tap blocks, so it multiplies samples back to p_begin/32*32 - 32*ceil(K/32) by taps that are
+    // zero padding - those samples must be initialised (0 * NaN = NaN), hence they are uploaded too.
+    long long lo = j->p_begin / 32 * 32 - 32LL * ((j->K + 31) / 32);
+    lo = lo < 0 ? 0 : lo;
     for (int i = 0; i < n_phases; ++i) {
         long long hi = p_cuts[i + 1] < j->n ? p_cuts[i + 1] : j->n;      // outputs < cut need inputs < cut
         if (hi > lo) {

@@ -7,7 +7,6 @@
 //
 // COMPILE THIS FILE WITH -fmad=false: a fused multiply-add would change floor()/ceil() inputs.
 #include <limits.h>
-#include <stdarg.h>
 
 #include "bas_internal.cuh"
 #include "plan_math.h"
@@ -16,35 +15,23 @@ static_assert(sizeof(BasTerm) == sizeof(bas_term), "term layout");
 static_assert(sizeof(BasTrace) == sizeof(bas_trace), "trace layout");
 static_assert(BAS_MAX_TERMS == 16 && BAS_N_DIR == BAS_N_DIRECTIONS, "constants");
 
-// ---- thread-local error string (defined once, here) -----------------------------------------
-static thread_local char g_err[512] = "";
-
-void bas_set_error(const char* fmt, ...) {
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(g_err, sizeof(g_err), fmt, ap);
-    va_end(ap);
-}
-
-extern "C" int bas_last_error(char* buf, size_t len) {
-    if (!buf || len == 0) return BAS_E_ARG;
-    strncpy(buf, g_err, len - 1);
-    buf[len - 1] = 0;
-    return 0;
-}
-
-extern "C" int bas_abi_version(void) { return BAS_ABI_VERSION; }
-
-extern "C" int bas_device_count(void) {
-    int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
-    return n;
-}
-
 // ---- device kernel ---------------------------------------------------------------------------
 // One thread per (trajectory point, ear): the ear-independent ring lookups are recomputed by both
 // threads of a point (cheap) so that all 2*n_points threads run independently; 64-thread CTAs spread
 // a 5169-point trajectory over every SM.
+// status[0]: OR of the error bits of every point; status[1]: min over failing points of
+// (index << 3 | error bits of that point, both ears) - the reference raises at the FIRST bad
+// trajectory point (apply_hrtf.py:429/:435 call interpolate_2d in time order), so the host needs the
+// bits of the earliest one.  The two ear threads of a point are neighbouring lanes.
+__device__ __forceinline__ void report_error(int* __restrict__ status, int err, long long idx) {
+    const int both = err | __shfl_xor_sync(__activemask(), err, 1);
+    if (both && status) {
+        atomicOr(status, both);
+        const long long capped = idx > BAS_STATUS_MAX_INDEX ? BAS_STATUS_MAX_INDEX : idx;
+        atomicMin(status + 1, (int)(capped << 3 | (both & 7)));
+    }
+}
+
 __device__ __forceinline__ void
 plan_thread(const double* __restrict__ diffs_l, const double* __restrict__ diffs_r, int U, long long L,
             double elev, double azim, int kind, long long p, int ear,
@@ -71,11 +58,7 @@ plan_thread(const double* __restrict__ diffs_l, const double* __restrict__ diffs
         __syncwarp();
         if (err) atomicOr(&tr->err, err);
     }
-    if (err && status) {
-        atomicOr(status, err);
-        const long long idx = p + point_offset;              // index reported to the caller
-        atomicMin(status + 1, (int)(idx > INT_MAX ? INT_MAX : idx));
-    }
+    report_error(status, err, p + point_offset);
 }
 
 __global__ void __launch_bounds__(64)
@@ -224,10 +207,7 @@ bas_plan_ring_kernel(const double* __restrict__ diffs_l, const double* __restric
         dst[k] = make_int4(local[2 * k].row_shift, __float_as_int(local[2 * k].weight),
                            local[2 * k + 1].row_shift, __float_as_int(local[2 * k + 1].weight));
     delays[2 * i + ear] = d;
-    if (err && status) {
-        atomicOr(status, err);
-        atomicMin(status + 1, (int)(i > INT_MAX ? INT_MAX : i));
-    }
+    report_error(status, err, i);
 }
 
 extern "C" int bas_plan_ring(const double* diffs_left_dev, const double* diffs_right_dev, int U, int L, const int* rows_dev,
@@ -262,4 +242,34 @@ extern "C" int bas_plan_ring_host(const double* diffs_left, const double* diffs_
         if (lo && hi) { lo[2 * e] = l2[0]; lo[2 * e + 1] = l2[1]; hi[2 * e] = h2[0]; hi[2 * e + 1] = h2[1]; }
     }
     return err;
+}
+
+// ---- delay_signal_float, apply_hrtf.py:127-165, as a callable of its own ----------------------
+// out[i] = (1 - a) * x[(i*D - before) mod n] + a * x[(i*D - after) mod n]: the two np.roll's (:156-157),
+// the decimation (:160-163) and the blend (:165) in float64, products rounded separately like numpy
+// (this file is compiled with -fmad=false), so the result is bit-identical to the reference's.
+__global__ void __launch_bounds__(256)
+bas_delay_signal_kernel(const double* __restrict__ x, long long n, long long before, long long after, double a,
+                        long long D, long long n_out, double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    long long ib = (i * D - before) % n, ia = (i * D - after) % n;
+    ib += ib < 0 ? n : 0;
+    ia += ia < 0 ? n : 0;
+    out[i] = (1 - a) * x[ib] + a * x[ia];
+}
+
+extern "C" int bas_delay_signal_float(const double* in_dev, long long n, long long before, long long after, double a,
+                                      int downsample, double* out_dev, void* stream) {
+    BAS_CHECK_ARG(in_dev && out_dev, "null pointer");
+    BAS_CHECK_ARG(n >= 0 && n < (1LL << 40), "n");
+    if (n == 0) return 0;
+    const long long D = downsample > 1 ? downsample : 1;            // :160 only decimates when downsample > 1
+    const long long n_out = (n + D - 1) / D;                        // len(np.arange(0, n, D))
+    const long long blocks = bas_ceil_div(n_out, 256);
+    BAS_CHECK_ARG(blocks < 0x7fffffffLL, "signal too long for one launch");
+    // reduce the shifts once on the host so the kernel's products cannot overflow
+    bas_delay_signal_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in_dev, n, before % n, after % n, a, D, n_out, out_dev);
+    BAS_LAUNCH_CHECK();
+    return 0;
 }

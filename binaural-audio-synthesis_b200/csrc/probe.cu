@@ -2,6 +2,7 @@
 // bench.py states the achieved FMA rate next to a MEASURED peak from this kernel (same clocks, same
 // box) instead of a nominal 148 SM x 128 lanes x clock figure.
 #include "bas_internal.cuh"
+#include "../../include/bas_probe.h"
 
 namespace {
 

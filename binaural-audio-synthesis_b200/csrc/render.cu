@@ -26,12 +26,14 @@
 //   math     Lane l of a warp owns the 32 consecutive outputs of block b = b0 + l for both ears: 32
 //            fma.rn.f32x2 accumulators {L,R}.  Output block b draws on input subchunks q = b - d:
 //                out[32b + r] += x[32q + m] * h_q[32d + r - m]          r, m = 0..31
-//            All lanes sit at the same (d, m), so subchunk boundaries are warp-uniform; each lane
-//            keeps a 32-entry ring of blended taps in registers and slides it one tap per m.  The
-//            half-empty first (d = 0, r >= m) and last (d = D, r < m) blocks are folded into ONE
-//            32x32 block whose ring is initialised from the d = 0 filter and refilled from the
-//            d = D filter, so a tile costs exactly ceil(K/32) blocks of 1024 packed FMAs plus 126
-//            blend operations each (89 % useful at K = 256, 94 % at K = 512).
+//            All lanes sit at the same (d, m), so subchunk boundaries are warp-uniform.  The 32x32
+//            products of a block are visited diagonal by diagonal (j = r - m fixed): ONE blended tap pair
+//            {L,R} is live at a time and feeds the 32 - |j| packed FMAs of its diagonal as the
+//            register-reuse operand; the lane's 32 input samples sit in registers (block_diag in
+//            render_tiled.cuh).  The half-empty first (d = 0, r >= m) and last (d = D, r < m) blocks are
+//            folded into ONE 32x32 block (diagonals >= 0 from the d = 0 filter, < 0 from the d = D
+//            filter), so a tile costs exactly ceil(K/32) blocks of 1024 packed FMAs plus 126 blend
+//            operations each (89 % useful at K = 256, 94 % at K = 512).
 //   taps     Blended on the fly: w = H_i + alpha (H_{i+1} - H_i) from two LDS.128 (two taps each);
 //            lanes in the same chunk read the same address (broadcast), other chunks other banks.
 //   epilogue Direct 16-byte global stores from registers, peak by warp reduction + one atomicMax.

@@ -89,11 +89,24 @@ __device__ __forceinline__ bool mbar_try_wait(void* bar, unsigned parity) {
         "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
-// Bounded: a copy that never lands (a wrong byte count, a bad pointer) must fail loudly, not hang the GPU.
-__device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
-    for (unsigned spins = 0; !mbar_try_wait(bar, parity); ++spins)
-        if (spins > (1u << 26)) __trap();
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
 }
+// Waits are bounded by ELAPSED TIME, not by a spin count: a copy that never lands (a wrong byte count, a
+// bad pointer) or a neighbour that never publishes must fail loudly instead of hanging the GPU, but a
+// healthy launch that is merely time-sliced (MPS, ncu replay, compute-sanitizer) or whose neighbour CTA
+// is not resident yet (other streams hold the SMs) must not be killed.
+constexpr unsigned long long kWaitLimitNs = 30ull * 1000 * 1000 * 1000;
+__device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const unsigned long long t0 = global_ns();
+    for (unsigned spins = 1; !mbar_try_wait(bar, parity); ++spins)
+        if ((spins & 1023u) == 0 && global_ns() - t0 > kWaitLimitNs) __trap();
+}
+// spin (lane 0 of a warp) until the neighbour CTA has published its partial stripe for this launch
+__device__ __forceinline__ void flag_wait(const unsigned long long* flag, unsigned long long epoch);
 // TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (UBLKCP in SASS)
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, void* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -238,6 +251,14 @@ __device__ __forceinline__ unsigned long long flag_acquire(const unsigned long l
     unsigned long long v;
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
     return v;
+}
+__device__ __forceinline__ void flag_wait(const unsigned long long* flag, unsigned long long epoch) {
+    if (flag_acquire(flag) == epoch) return;
+    const unsigned long long t0 = global_ns();
+    for (unsigned spins = 1; flag_acquire(flag) != epoch; ++spins) {
+        __nanosleep(64);
+        if ((spins & 1023u) == 0 && global_ns() - t0 > kWaitLimitNs) __trap();     // the neighbour never published
+    }
 }
 // workspace: one flag and one stripe of {L,R} partial sums per (CTA, stripe)
 __host__ __device__ inline size_t ws_flag_bytes(long long grid, int TS) { return ((size_t)grid * TS * 8 + 255) / 256 * 256; }
@@ -504,13 +525,7 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
         u64* ws_sums = reinterpret_cast<u64*>(reinterpret_cast<unsigned char*>(workspace) + ws_flag_bytes(gridDim.x, TS));
         if (!MIX && adopt && it.group_end && warp_live) {
             const long long slot = (long long)(blockIdx.x + 1) * TS + stripe;
-            if (lane == 0) {
-                unsigned spins = 0;
-                while (flag_acquire(ws_flags + slot) != sp.epoch) {
-                    __nanosleep(64);
-                    if (++spins > (1u << 24)) __trap();             // the neighbour never published: fail loudly
-                }
-            }
+            if (lane == 0) flag_wait(ws_flags + slot, sp.epoch);
             __syncwarp();
             const u64* srcp = ws_sums + slot * kWarpTile + lane;
 #pragma unroll
@@ -539,13 +554,7 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
             }
             if (adopt && it.group_end && warp_live) {           // earlier sources (here) + later sources (next CTA)
                 const long long slot = (long long)(blockIdx.x + 1) * TS + stripe;
-                if (lane == 0) {
-                    unsigned spins = 0;
-                    while (flag_acquire(ws_flags + slot) != sp.epoch) {
-                        __nanosleep(64);
-                        if (++spins > (1u << 24)) __trap();
-                    }
-                }
+                if (lane == 0) flag_wait(ws_flags + slot, sp.epoch);
                 __syncwarp();
                 const u64* srcp = ws_sums + slot * kWarpTile + lane;
 #pragma unroll

@@ -25,3 +25,30 @@ extern "C" int bas_memset(void* dev, int value, long long bytes, void* stream) {
     if (bytes) BAS_CUDA(cudaMemsetAsync(dev, value, (size_t)bytes, (cudaStream_t)stream));
     return 0;
 }
+
+// Page-lock a caller's host array in place so that the upload of make_signal_move_2d's input
+// (apply_hrtf.py:356: in_signal is an ordinary, pageable ndarray) is a direct DMA instead of a
+// staged copy.  The Python host keeps one registration per live array (dropped when the array dies).
+extern "C" int bas_host_register(void* host, long long bytes) {
+    BAS_CHECK_ARG(host && bytes > 0, "bad pointer or size");
+    cudaError_t e = cudaHostRegister(host, (size_t)bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return 0; }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        bas_set_error("bas_host_register: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+
+extern "C" int bas_host_unregister(void* host) {
+    BAS_CHECK_ARG(host, "null pointer");
+    cudaError_t e = cudaHostUnregister(host);
+    if (e != cudaSuccess && e != cudaErrorHostMemoryNotRegistered) {
+        cudaGetLastError();
+        bas_set_error("bas_host_unregister: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    cudaGetLastError();
+    return 0;
+}

@@ -14,22 +14,7 @@ import numpy as np
 
 from . import _cabi
 
-RING_ELEV_DEG = (-45, -30, -15, 0, 15, 30, 45, 60, 75, 90)
-RING_COUNT = (24, 24, 24, 24, 24, 24, 24, 12, 6, 1)
-
-
-def get_index_elev_azim() -> np.ndarray:
-    """sphere.py:124-319."""
-    rows = []
-    index = 0
-    for elev, count in zip(RING_ELEV_DEG, RING_COUNT):
-        for k in range(count):
-            rows.append((index, elev, k * (360 // count) if count > 1 else 0))
-            index += 1
-    table = np.array(rows, dtype=np.float32)
-    table[:, 1:3] *= (2 * np.pi / 360)          # float32 multiply, like sphere.py:318
-    return table
-
+from ._grid import RING_ELEV_DEG, RING_COUNT, get_index_elev_azim          # noqa: F401  (pure numpy, no library)
 
 index_elev_azim = get_index_elev_azim()            # module global, like sphere.py:350
 

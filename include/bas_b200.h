@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define BAS_ABI_VERSION 2
+#define BAS_ABI_VERSION 3
 
 #define BAS_N_DIRECTIONS 187      /* rows of the measurement grid, sphere.py:127-315 */
 #define BAS_MAX_TERMS 16          /* merged gather terms per ear per trajectory point */
@@ -86,7 +86,11 @@ int bas_bank_delay_diffs(const double* hrir_dev, int n_rows, int n, int U, const
  * diffs_*_dev: 187 x 187 doubles row-major.  elev/azim: n_points doubles (radians).
  * az_kind_dev: n_points bytes (BAS_AZ_*), or NULL to use az_kind_all for every point.
  * terms_dev:   n_points x 2 x BAS_MAX_TERMS.   trace_dev: n_points records or NULL.
- * status_dev:  2 ints: OR of all error bits, and the lowest failing point index (or INT_MAX). */
+ * status_dev:  2 ints: [0] OR of the error bits of all points; [1] the minimum over failing points of
+ *              (point index << 3 | error bits of that point) - index and bits of the EARLIEST failing
+ *              point, which is where the reference would have raised (0x7f7f7f7f when none failed;
+ *              indices are capped at BAS_STATUS_MAX_INDEX). */
+#define BAS_STATUS_MAX_INDEX 0x0fffffff
 int bas_plan_build(const double* diffs_left_dev, const double* diffs_right_dev, int U, int L,
                    const double* elev_dev, const double* azim_dev, const uint8_t* az_kind_dev,
                    int az_kind_all, long long n_points, bas_term* terms_dev, bas_trace* trace_dev,
@@ -120,6 +124,15 @@ int bas_plan_ring(const double* diffs_left_dev, const double* diffs_right_dev, i
 int bas_plan_ring_host(const double* diffs_left, const double* diffs_right, int U, int L, int before,
                        int after, double alpha, double one_minus_alpha, bas_term* terms,
                        double* delays, int64_t* lo, int64_t* hi);
+
+/* ---- delay_signal_float, apply_hrtf.py:127-165, as a callable of its own (inside interpolate_2d its
+ *      gathers are fused into bas_ir_synth) ----------------------------------------------------
+ * in_dev: n doubles.  before = int(floor(samples)), after = int(ceil(samples)), a = samples - before are
+ * evaluated by the caller exactly as :149-151 do.  out_dev: ceil(n / D) doubles, D = max(downsample, 1):
+ *     out[i] = (1 - a) * in[(i*D - before) mod n] + a * in[(i*D - after) mod n]
+ * (circular like np.roll, :156-157; float64, products rounded separately: bit-identical to numpy). */
+int bas_delay_signal_float(const double* in_dev, long long n, long long before, long long after, double a,
+                           int downsample, double* out_dev, void* stream);
 
 /* ---- IR synthesis: the array part of interpolate_2d (apply_hrtf.py:219-281) and of
  *      delay_compensated_interpolation_with_delaydiff (apply_hrtf.py:86-102) ------------------
@@ -186,6 +199,13 @@ int bas_peak(const float* v_dev, long long n, float* peak_dev, void* stream);
 int bas_copy_2d(void* dst, long long dst_pitch_bytes, const void* src, long long src_pitch_bytes,
                 long long width_bytes, long long rows, int to_device, void* stream);
 
+/* Page-lock / release a caller-owned host array in place (cudaHostRegister): the input signal of
+ * make_signal_move_2d (apply_hrtf.py:356) is an ordinary pageable ndarray; registered once, its
+ * upload is a direct DMA.  Registering an already registered range, or releasing an unregistered
+ * one, succeeds. */
+int bas_host_register(void* host, long long bytes);
+int bas_host_unregister(void* host);
+
 /* ---- make_signal_move_2d with host buffers (apply_hrtf.py:356-466): upload, plan, ir_synth,
  *      segmented render and download as one pipeline over three streams ------------------------
  * The output range is cut into 1..8 PHASES along time (p_cuts[0..n_phases]).
@@ -246,22 +266,6 @@ int bas_pipeline_trace(int enable, char* buf, size_t len);
 
 /* Asynchronous byte fill of device memory on `stream` (zeroing peaks before bas_render). */
 int bas_memset(void* dev, int value, long long bytes, void* stream);
-
-/* FP32 pipe probe used by bench.py to state the measured FMA peak beside the HBM roofline:
- * every thread runs `iters` rounds of 16 independent dependent-chain FMAs.
- * packed=0: fma.rn.f32 (32 FMA per thread per round) ; packed=1: fma.rn.f32x2 (same FMA count).
- * sink_dev receives one float per thread so the work cannot be elided.  FMA count of the launch =
- * blocks * threads * iters * 32. */
-int bas_probe_fma(int packed, int blocks, int threads, int iters, float* sink_dev, void* stream);
-
-/* bas_probe_fma (packed = 0 / 1) that also reports the SM clock (MHz) the stream ran at, measured on the
- * device (clock64 against the nanosecond global timer): what the FMA peak has to be read against. */
-int bas_probe_clock(int packed, int blocks, int threads, int iters, float* sink_dev, float* mhz_dev, void* stream);
-
-/* The render kernel's own 32x32 block on synthetic shared-memory data, without the tile machinery:
- * `blocks` CTAs of 4 warps, every warp runs iters x 6 blocks of 1024 useful packed FMAs per lane.
- * ctas_per_sm (1..3) selects the register budget the block is compiled for. */
-int bas_probe_block(int ctas_per_sm, int blocks, int iters, float* sink_dev, void* stream);
 
 #ifdef __cplusplus
 }

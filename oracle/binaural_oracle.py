@@ -130,6 +130,11 @@ def circular_delay(sig: np.ndarray, d, step: int = 1) -> np.ndarray:
     return (1 - frac) * sig[(n - lo) % size] + frac * sig[(n - hi) % size]
 
 
+def delay_signal_float(in_sig, samples, downsample=1) -> np.ndarray:
+    """apply_hrtf.py:127-165 under the reference's own name and signature (circular_delay above)."""
+    return circular_delay(np.asarray(in_sig), samples, int(downsample))
+
+
 # --------------------------------------------------------------------------------------
 # ring (1-D) interpolation  (apply_hrtf.py:53-106)
 # --------------------------------------------------------------------------------------

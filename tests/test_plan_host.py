@@ -33,7 +33,21 @@ def test_header_symbols_exported(bas):
     for name in declared:
         assert hasattr(lib, name), name
     assert declared == set(bas._cabi.EXPORTS)
-    assert lib.bas_abi_version() == bas._cabi.ABI_VERSION == 2
+    assert lib.bas_abi_version() == bas._cabi.ABI_VERSION == 3
+
+
+def test_probe_library_is_separate(bas):
+    """Measurement kernels live in libbas_probe.so (include/bas_probe.h); the product library exports none."""
+    import os
+    root = os.path.dirname(bas._cabi._HERE)
+    header = open(os.path.join(root, 'include', 'bas_probe.h')).read()
+    declared = set(re.findall(r'^int (bas_probe_\w+)\(', header, flags=re.M))
+    assert declared
+    probe = C.CDLL(os.path.join(bas._cabi._HERE, 'libbas_probe.so'))
+    product = C.CDLL(bas._cabi.LIB_PATH)
+    for name in declared:
+        assert hasattr(probe, name), name
+        assert not hasattr(product, name), name
 
 
 def test_ring_lookup_host_bit_exact(bas, golden):

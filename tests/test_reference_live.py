@@ -57,3 +57,4 @@ def test_render_matches_live_reference(ref, oracle, golden_bank):
     got = oracle.make_signal_move_2d(x, 256, 32, traj, golden_bank)
     assert got.shape == want.shape
     assert np.linalg.norm(got - want) <= 2e-7 * np.linalg.norm(want)
+

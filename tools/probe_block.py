@@ -4,7 +4,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 from binaural_audio_synthesis_b200 import _cabi
-lib = _cabi.lib
+sys.path.insert(0, os.path.join(ROOT, 'tools'))
+import probe_lib
+lib = probe_lib.load()
 sink = torch.empty(148 * 3 * 128, dtype=torch.float32, device='cuda')
 st = torch.cuda.current_stream().cuda_stream
 out = {}

@@ -9,7 +9,9 @@ sys.path.insert(0, ROOT)
 import torch
 from binaural_audio_synthesis_b200 import _cabi
 
-lib = _cabi.lib
+sys.path.insert(0, os.path.join(ROOT, 'tools'))
+import probe_lib
+lib = probe_lib.load()
 dev = torch.device('cuda', 0)
 stream = torch.cuda.current_stream().cuda_stream
 sink = torch.empty(148 * 64 * 256, dtype=torch.float32, device=dev)
