@@ -61,7 +61,24 @@ class PipelineJob(C.Structure):
                 ('out_host', C.c_void_p), ('small_host', C.c_void_p),
                 ('arena_dev', C.c_void_p), ('arena_bytes', C.c_longlong),
                 ('workspace_dev', C.c_void_p), ('workspace_bytes', C.c_longlong),
-                ('stream_main', C.c_void_p), ('stream_up', C.c_void_p), ('stream_down', C.c_void_p)]
+                ('stream_main', C.c_void_p), ('stream_up', C.c_void_p), ('stream_down', C.c_void_p),
+                ('bank_pp2_dev', C.c_void_p)]
+
+
+STEP_PLAN, STEP_RENDER, STEP_NORMALISE, STEP_FUSED = 1, 2, 4, 8
+
+
+class StepJob(C.Structure):
+    """bas_step_job (include/bas_b200.h)."""
+    _fields_ = [('n_src', C.c_int), ('C', C.c_int), ('S', C.c_int), ('K', C.c_int), ('U', C.c_int), ('mix', C.c_int),
+                ('variant', C.c_int), ('az_kind_all', C.c_int), ('flags', C.c_int), ('reserved', C.c_int),
+                ('n_valid', C.c_longlong), ('n_in', C.c_longlong), ('x_stride', C.c_longlong),
+                ('p_begin', C.c_longlong), ('p_count', C.c_longlong), ('out_stride', C.c_longlong),
+                ('x_dev', C.c_void_p), ('elev_dev', C.c_void_p), ('azim_dev', C.c_void_p), ('az_kind_dev', C.c_void_p),
+                ('diffs_left_dev', C.c_void_p), ('diffs_right_dev', C.c_void_p), ('bank_pp_dev', C.c_void_p),
+                ('bank_pp2_dev', C.c_void_p), ('terms_dev', C.c_void_p), ('filt_dev', C.c_void_p), ('gains_dev', C.c_void_p),
+                ('out_dev', C.c_void_p), ('small_dev', C.c_void_p), ('workspace_dev', C.c_void_p),
+                ('workspace_bytes', C.c_longlong)]
 
 
 class BasError(RuntimeError):
@@ -91,6 +108,10 @@ def _load():
         'bas_ir_synth': ([vp, i, i, vp, ll, i, vp, ll, vp], i),
         'bas_filter_row_pitch': ([i], i),
         'bas_render': ([vp, ll, ll, i, ll, i, i, i, vp, vp, ll, ll, vp, ll, i, vp, i, vp, ll, vp], i),
+        'bas_render_fused': ([vp, ll, ll, i, ll, i, i, i, vp, vp, i, vp, ll, ll, vp, ll, i, vp, i, vp, ll, vp], i),
+        'bas_render_fused_supported': ([i, i], i),
+        'bas_bank2_floats': ([i, i], ll),
+        'bas_render_step': ([C.POINTER(StepJob), vp], i),
         'bas_render_workspace_bytes': ([], ll),
         'bas_normalise': ([vp, ll, vp, vp], i),
         'bas_peak': ([vp, ll, vp, vp], i),
@@ -126,7 +147,7 @@ def decode_status(words):
     launch (include/bas_b200.h): the reference raises at the first bad trajectory point."""
     if not int(words[0]):
         return 0, 0
-    packed = int(words[1])
+    packed = ~int(words[1]) & 0xffffffff             # stored complemented, so that zeroed words mean "no error"
     return packed & 7, packed >> 3
 
 

@@ -60,6 +60,11 @@ class _BankDevice:
             staged = torch.from_numpy(irs).to(device)
             _cabi.check(lib.bas_bank_to_polyphase(staged.data_ptr(), _cabi.N_DIRECTIONS, length, u,
                                                   self.bank_pp[ear].data_ptr(), stream), 'bas_bank_to_polyphase')
+        # the same bank with every phase row stored twice in a row (+ padding): the layout bas_render_fused
+        # gathers from ((m - adv) mod K becomes the plain index m + K - adv).  A copy, not arithmetic.
+        self.bank_pp2 = torch.zeros(int(lib.bas_bank2_floats(u, self.taps)), dtype=torch.float32, device=device)
+        self.bank_pp2[:2 * _cabi.N_DIRECTIONS * u * 2 * self.taps].view(2, _cabi.N_DIRECTIONS, u, 2, self.taps).copy_(
+            self.bank_pp.unsqueeze(3).expand(2, _cabi.N_DIRECTIONS, u, 2, self.taps))
         torch.cuda.current_stream(device).synchronize()     # staged fp64 rows may now be freed
 
 
@@ -452,7 +457,6 @@ def _scratch(torch, shape, dtype, device):
         t.view(torch.uint8).fill_(0xff)
     return t
 
-MIX_GROUP_SOURCES = 16           # mixing more sources than this: groups, planned / synthesised while the previous group renders
 
 
 def _streams(torch, device):
@@ -608,6 +612,81 @@ def _phase_plan(p0: int, p1: int, n_in: int, chunksize: int, out_bytes_per_sampl
     return phases
 
 
+FUSED = True                     # let the render kernel synthesise its filter rows (bas_render_fused) where it can;
+                                 # False: bas_ir_synth writes filter rows to HBM first (same rows, bit for bit)
+
+
+class DeviceRender:
+    """Sources resident in HBM, planned once, rendered range by range: the device half of
+    render_sources, also driven by distributed.py (which interleaves collectives with the ranges).
+
+    x: CUDA float32 (n_src, n_in) zero padded; elev_d / azim_d: CUDA float64 n_src * n_pts directions.
+    plan() enqueues memset + bas_plan_build (+ bas_ir_synth unless fused) through bas_render_step;
+    render(pa, pb, out_ptr, out_stride) enqueues the render of output samples [pa, pb)."""
+
+    def __init__(self, torch, dev, x, n_in, chunksize, subchunksize, elev_d, azim_d, kinds, mix, variant):
+        self.torch, self.dev, self.x = torch, dev, x
+        device = dev.device
+        n_src = x.shape[0]
+        n_pts = n_in // chunksize + 1
+        self.n_src, self.n_pts, self.mix = n_src, n_pts, mix
+        self.elev_d, self.azim_d = elev_d, azim_d
+        self.kinds_d = None if np.isscalar(kinds) else torch.as_tensor(
+            np.ascontiguousarray(kinds, dtype=np.uint8).reshape(-1)).to(device)
+        if self.kinds_d is not None and self.kinds_d.numel() != n_src * n_pts:
+            raise ValueError('az_kind must have one entry per direction')
+        self.fused = bool(FUSED and (variant & 0x3f) != _cabi.RENDER_GENERIC and lib.bas_render_fused_supported(chunksize, subchunksize)
+                          and x.data_ptr() % 16 == 0 and (n_src == 1 or x.stride(0) % 4 == 0))
+        self.terms = torch.empty(n_src * n_pts * 2 * _cabi.MAX_TERMS * 8, dtype=torch.uint8, device=device)
+        self.filt = None if self.fused else torch.empty((n_src * n_pts, lib.bas_filter_row_pitch(dev.taps), 2),
+                                                        dtype=torch.float32, device=device)
+        self.small = torch.empty(2 + n_src, dtype=torch.int32, device=device)      # zeroed by plan()
+        self.peaks = self.small[2:].view(torch.float32)
+        self.workspace = _cabi.render_workspace(torch, device)
+        self.job = _cabi.StepJob(
+            n_src=n_src, C=chunksize, S=subchunksize, K=dev.taps, U=dev.upsampling, mix=1 if mix else 0, variant=variant,
+            az_kind_all=_cabi.AZ_F64 if self.kinds_d is not None else int(kinds), flags=0,
+            n_valid=n_in, n_in=n_in, x_stride=x.stride(0) if n_src > 1 else n_in, p_begin=0, p_count=0, out_stride=0,
+            x_dev=x.data_ptr(), elev_dev=elev_d.data_ptr(), azim_dev=azim_d.data_ptr(),
+            az_kind_dev=self.kinds_d.data_ptr() if self.kinds_d is not None else None,
+            diffs_left_dev=dev.diffs[0].data_ptr(), diffs_right_dev=dev.diffs[1].data_ptr(), bank_pp_dev=dev.bank_pp.data_ptr(),
+            bank_pp2_dev=dev.bank_pp2.data_ptr(), terms_dev=self.terms.data_ptr(),
+            filt_dev=self.filt.data_ptr() if self.filt is not None else None, gains_dev=None, out_dev=None,
+            small_dev=self.small.data_ptr(), workspace_dev=self.workspace.data_ptr(), workspace_bytes=self.workspace.numel())
+        self._fused_flag = _cabi.STEP_FUSED if self.fused else 0
+
+    def plan(self, stream):
+        self.job.flags = _cabi.STEP_PLAN | self._fused_flag
+        self.job.p_count = 0
+        _cabi.check(lib.bas_render_step(C.byref(self.job), stream), 'bas_render_step')
+
+    def render(self, stream, pa, pb, out_ptr, out_stride, gains=None, accumulate=False, normalise=False):
+        job = self.job
+        job.flags = _cabi.STEP_RENDER | self._fused_flag | (_cabi.STEP_NORMALISE if normalise else 0)
+        job.p_begin, job.p_count, job.out_dev, job.out_stride = pa, pb - pa, out_ptr, out_stride
+        job.gains_dev = gains.data_ptr() if gains is not None else None
+        job.mix = (_cabi.MIX_ACCUMULATE if accumulate else 1) if self.mix else 0
+        rc = lib.bas_render_step(C.byref(job), stream)
+        if rc == _cabi.E_UNSUPPORTED and self.fused:
+            # no tile shape of the fused kernel fits this geometry: write the filter rows to HBM after all
+            # and let bas_render choose (its generic kernel takes any chunk / subchunk / tap count)
+            self._unfuse(stream)
+            job.flags &= ~_cabi.STEP_FUSED
+            rc = lib.bas_render_step(C.byref(job), stream)
+        _cabi.check(rc, 'bas_render_step')
+
+    def _unfuse(self, stream):
+        dev, torch = self.dev, self.torch
+        self.fused, self._fused_flag = False, 0
+        self.filt = torch.empty((self.n_src * self.n_pts, lib.bas_filter_row_pitch(dev.taps), 2), dtype=torch.float32, device=dev.device)
+        self.job.filt_dev = self.filt.data_ptr()
+        _cabi.check(lib.bas_ir_synth(dev.bank_pp.data_ptr(), dev.upsampling, dev.taps, self.terms.data_ptr(), self.n_src * self.n_pts,
+                                     _cabi.IR_ROWS, self.filt.data_ptr(), dev.taps, stream), 'bas_ir_synth')
+
+    def zero_peaks(self):
+        self.peaks.zero_()
+
+
 def _render_pipeline(torch, dev, src, chunksize, subchunksize, elev_azim_functions, mix, normalise, variant,
                      p0, p1, return_peaks):
     """render_sources for host signals and a host result: lib.bas_pipeline_upload / _phase."""
@@ -638,7 +717,9 @@ def _render_pipeline(torch, dev, src, chunksize, subchunksize, elev_azim_functio
         diffs_right_dev=dev.diffs[1].data_ptr(), bank_pp_dev=dev.bank_pp.data_ptr(), out_host=host_out.data_ptr(),
         small_host=small.data_ptr(), arena_dev=arena.data_ptr(), arena_bytes=arena.numel(),
         workspace_dev=workspace.data_ptr(), workspace_bytes=workspace.numel(),
-        stream_main=main.cuda_stream, stream_up=up.cuda_stream, stream_down=down.cuda_stream)
+        stream_main=main.cuda_stream, stream_up=up.cuda_stream, stream_down=down.cuda_stream,
+        bank_pp2_dev=dev.bank_pp2.data_ptr() if FUSED else None)
+    fused = bool(FUSED and (variant & 0x3f) != _cabi.RENDER_GENERIC and lib.bas_render_fused_supported(chunksize, subchunksize))
     phases = _phase_plan(p0, p1, n_in, chunksize, 8 * n_rows)
     cuts = (C.c_longlong * (len(phases) + 1))(*([ph[0] for ph in phases] + [p1]))
     _cabi.check(lib.bas_pipeline_upload(C.byref(job), len(phases), cuts), 'bas_pipeline_upload')
@@ -685,9 +766,14 @@ def _render_pipeline(torch, dev, src, chunksize, subchunksize, elev_azim_functio
         out_dev, peaks_dev, stream = base + offsets[6], base + offsets[4] + 8, main.cuda_stream
         if mix:
             gains = torch.from_numpy((1.0 / np.maximum(peaks_host, 1.0)).astype(np.float32)).to(device)
-            _cabi.check(lib.bas_render(base + offsets[5], n_in, n_in, n_src, n_in, chunksize, subchunksize, k, base + offsets[3],
-                                       gains.data_ptr(), p0, count, out_dev, stride, 1, None, variant, workspace.data_ptr(),
-                                       workspace.numel(), stream), 'bas_render')
+            if fused:
+                _cabi.check(lib.bas_render_fused(base + offsets[5], n_in, n_in, n_src, n_in, chunksize, subchunksize, k, base + offsets[2],
+                                                 dev.bank_pp2.data_ptr(), dev.upsampling, gains.data_ptr(), p0, count, out_dev, stride, 1,
+                                                 None, variant, workspace.data_ptr(), workspace.numel(), stream), 'bas_render_fused')
+            else:
+                _cabi.check(lib.bas_render(base + offsets[5], n_in, n_in, n_src, n_in, chunksize, subchunksize, k, base + offsets[3],
+                                           gains.data_ptr(), p0, count, out_dev, stride, 1, None, variant, workspace.data_ptr(),
+                                           workspace.numel(), stream), 'bas_render')
         else:
             for s in np.nonzero(peaks_host > 1)[0]:
                 _cabi.check(lib.bas_normalise(out_dev + int(s) * 8 * stride, 2 * stride, peaks_dev + 4 * int(s), stream), 'bas_normalise')
@@ -794,63 +880,16 @@ def render_sources(signals, chunksize: int, subchunksize: int, elev_azim_functio
         elev_d, azim_d = both[0], both[1]
     if elev_d.numel() != n_src * n_pts or azim_d.numel() != n_src * n_pts:
         raise ValueError('trajectories must give %d directions per source' % n_pts)
-    # status (2 ints) and per-source peaks share one buffer: one memset, one copy back
-    small_dev = torch.zeros(2 + n_src, dtype=torch.int32, device=device)
-    status, peaks = small_dev[:2], small_dev[2:].view(torch.float32)
     stride = _round_up(max(count, 1), 4)
     n_rows = 1 if mix else n_src
     out = torch.empty((n_rows, 2, stride), dtype=torch.float32, device=device)
-    workspace = _cabi.render_workspace(torch, device)
-    grouped = mix and return_device and n_src > MIX_GROUP_SOURCES and count > 0
-    if not grouped:
-        filt, _, _ = _plan_and_synth(torch, dev, elev_d, azim_d, kinds, n_src * n_pts, _cabi.IR_ROWS, status=status)
-        if uploaded is not None:
-            main.wait_event(uploaded)
+    job = DeviceRender(torch, dev, x, n_in, chunksize, subchunksize, elev_d.reshape(-1), azim_d.reshape(-1), kinds, mix, variant)
+    job.plan(stream)
+    if uploaded is not None:
+        main.wait_event(uploaded)
 
-        def launch(gains, pa, pb):
-            _cabi.check(lib.bas_render(x.data_ptr(), n_in, n_in, n_src, n_in, chunksize, subchunksize, k,
-                                       filt.data_ptr(), gains.data_ptr() if gains is not None else None,
-                                       pa, pb - pa, out.data_ptr() + 4 * (pa - p0), stride, 1 if mix else 0, peaks.data_ptr(),
-                                       variant, workspace.data_ptr(), workspace.numel(), stream), 'bas_render')
-    else:
-        # Many sources mixed into one output: groups of sources are planned and synthesised (latency /
-        # L2 bound) on a side stream while the previous group renders (FP32-pipe bound) on the main one;
-        # every group after the first ADDS its mix to the output (BAS_MIX_ACCUMULATE), groups in order.
-        if uploaded is not None:
-            main.wait_event(uploaded)
-        elev_f, azim_f = elev_d.reshape(-1), azim_d.reshape(-1)
-        kinds_d = None if np.isscalar(kinds) else torch.as_tensor(np.ascontiguousarray(kinds, dtype=np.uint8).reshape(-1)).to(device)
-        g_pts = MIX_GROUP_SOURCES * n_pts
-        pitch = lib.bas_filter_row_pitch(k)
-        terms_buf = [torch.empty(g_pts * 2 * _cabi.MAX_TERMS * 8, dtype=torch.uint8, device=device) for _ in range(2)]
-        filt_buf = [torch.empty((g_pts, pitch, 2), dtype=torch.float32, device=device) for _ in range(2)]
-        groups = [(s0, min(n_src, s0 + MIX_GROUP_SOURCES)) for s0 in range(0, n_src, MIX_GROUP_SOURCES)]
-        status_all = torch.zeros((len(groups), 2), dtype=torch.int32, device=device)
-
-        def launch(gains, pa, pb):
-            up.wait_stream(main)                                 # buffers above were allocated on `main`
-            rendered = [None, None]
-            for gi, (s0, s1) in enumerate(groups):
-                b, m = gi & 1, (s1 - s0) * n_pts
-                if rendered[b] is not None:
-                    up.wait_event(rendered[b])                   # the render two groups back has left this buffer
-                _cabi.check(lib.bas_plan_build(dev.diffs[0].data_ptr(), dev.diffs[1].data_ptr(), dev.upsampling, dev.length,
-                                               elev_f.data_ptr() + 8 * s0 * n_pts, azim_f.data_ptr() + 8 * s0 * n_pts,
-                                               kinds_d.data_ptr() + s0 * n_pts if kinds_d is not None else None,
-                                               0 if kinds_d is not None else int(kinds), m, terms_buf[b].data_ptr(), None,
-                                               status_all[gi].data_ptr(), up.cuda_stream), 'bas_plan_build')
-                _cabi.check(lib.bas_ir_synth(dev.bank_pp.data_ptr(), dev.upsampling, k, terms_buf[b].data_ptr(), m, _cabi.IR_ROWS,
-                                             filt_buf[b].data_ptr(), k, up.cuda_stream), 'bas_ir_synth')
-                ready = torch.cuda.Event()
-                ready.record(up)
-                main.wait_event(ready)
-                _cabi.check(lib.bas_render(x.data_ptr() + 4 * s0 * n_in, n_in, n_in, s1 - s0, n_in, chunksize, subchunksize, k,
-                                           filt_buf[b].data_ptr(), gains.data_ptr() + 4 * s0 if gains is not None else None,
-                                           pa, pb - pa, out.data_ptr() + 4 * (pa - p0), stride, 1 if gi == 0 else _cabi.MIX_ACCUMULATE,
-                                           peaks.data_ptr() + 4 * s0, variant, workspace.data_ptr(), workspace.numel(), stream),
-                            'bas_render')
-                rendered[b] = torch.cuda.Event()
-                rendered[b].record(main)
+    def launch(gains, pa, pb, normalise_now=False):
+        job.render(stream, pa, pb, out.data_ptr() + 4 * (pa - p0), stride, gains=gains, normalise=normalise_now)
 
     small = torch.empty(2 + n_src, dtype=torch.int32, pin_memory=True)
     host_out = None if return_device else torch.empty((n_rows, 2, count), dtype=torch.float32, pin_memory=True)
@@ -861,7 +900,7 @@ def render_sources(signals, chunksize: int, subchunksize: int, elev_azim_functio
                                     4 * (pb - pa), 2 * n_rows, 0, st.cuda_stream), 'bas_copy_2d')
 
     def fetch_small(st):
-        _cabi.check(lib.bas_copy_2d(small.data_ptr(), 0, small_dev.data_ptr(), 0, 4 * (2 + n_src), 1, 0, st.cuda_stream), 'bas_copy_2d')
+        _cabi.check(lib.bas_copy_2d(small.data_ptr(), 0, job.small.data_ptr(), 0, 4 * (2 + n_src), 1, 0, st.cuda_stream), 'bas_copy_2d')
 
     if host_out is not None and count > 0:
         # ---- pipeline: segment i is downloaded while segment i+1 renders ------------------------------
@@ -877,22 +916,13 @@ def render_sources(signals, chunksize: int, subchunksize: int, elev_azim_functio
         second_pass = normalise
     else:
         if count > 0:
-            launch(None, p0, p1)
-            if normalise and not mix:     # apply_hrtf.py:462-464 per source, peak read on the device
-                for s in range(n_src):
-                    _cabi.check(lib.bas_normalise(out[s].data_ptr(), 2 * stride, peaks[s:s + 1].data_ptr(), stream), 'bas_normalise')
+            launch(None, p0, p1, normalise_now=normalise and not mix)   # apply_hrtf.py:462-464 per source, peak read on the device
         second_pass = normalise and mix
         fetch_small(main)
         main.synchronize()
 
     host = small.numpy()
     err, where = _cabi.decode_status(host)
-    if grouped:                                  # one status pair per source group: first failing direction overall
-        per_group = status_all.cpu().numpy()
-        failing = np.nonzero(per_group[:, 0])[0]
-        if failing.size:
-            err, where = _cabi.decode_status(per_group[failing[0]])
-            where += int(failing[0]) * MIX_GROUP_SOURCES * n_pts
     if err:
         _raise_plan_error(err, ' (trajectory point %d of source %d)' % (where % n_pts, where // n_pts))
     peaks_host = host[2:].view(np.float32).copy()
@@ -901,11 +931,11 @@ def render_sources(signals, chunksize: int, subchunksize: int, elev_azim_functio
     if second_pass and count > 0 and (peaks_host > 1).any():
         if mix:
             gains = torch.from_numpy((1.0 / np.maximum(peaks_host, 1.0)).astype(np.float32)).to(device)
-            peaks.zero_()
+            job.zero_peaks()
             launch(gains, p0, p1)
         else:
             for s in np.nonzero(peaks_host > 1)[0]:
-                _cabi.check(lib.bas_normalise(out[int(s)].data_ptr(), 2 * stride, peaks[int(s):int(s) + 1].data_ptr(), stream),
+                _cabi.check(lib.bas_normalise(out[int(s)].data_ptr(), 2 * stride, job.peaks[int(s):int(s) + 1].data_ptr(), stream),
                             'bas_normalise')
         if host_out is not None:
             download(p0, p1, main)

@@ -45,3 +45,35 @@ int bas_plan_build_inline(const double* diffs_left_dev, const double* diffs_righ
                           bas_term* terms_dev, int* status_dev, long long point_offset, void* stream);
 
 static inline long long bas_ceil_div(long long a, long long b) { return (a + b - 1) / b; }
+
+// ---- programmatic dependent launch ---------------------------------------------------------------
+// bas_render_step chains plan -> ir_synth -> render -> normalise on one stream.  Inside such a chain a
+// kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs may become resident
+// while the previous kernel drains (launch latency, barrier / table set-up overlap its tail), and
+// bas_grid_dependency_wait() - griddepcontrol.wait, the first thing each kernel does before it touches
+// anything an earlier kernel wrote or still reads - holds them until that kernel has completed and
+// flushed.  Outside a chain (the flag is off) kernels launch with full stream serialization and the
+// wait returns at once.  The flag is per host thread; bas_render_step sets it around its launches.
+bool& bas_pdl_flag();
+struct BasPdlScope {
+    bool saved;
+    explicit BasPdlScope(bool on) : saved(bas_pdl_flag()) { bas_pdl_flag() = on; }
+    ~BasPdlScope() { bas_pdl_flag() = saved; }
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void bas_grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void bas_grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t bas_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = bas_pdl_flag() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif

@@ -26,3 +26,8 @@ extern "C" int bas_device_count(void) {
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
 }
+
+bool& bas_pdl_flag() {
+    static thread_local bool on = false;
+    return on;
+}

@@ -27,6 +27,8 @@ constexpr int kMaxTerms = BAS_MAX_TERMS;
 __global__ void __launch_bounds__(kThreads)
 bas_ir_synth_kernel(const float* __restrict__ bank_pp, int U, int K, const BasTermDev* __restrict__ terms,
                     float* __restrict__ out, long long out_stride) {
+    bas_grid_launch_dependents();
+    bas_grid_dependency_wait();
     const long long point = blockIdx.x;
     const int ear = blockIdx.y;
     const int L = U * K;
@@ -75,6 +77,8 @@ bas_ir_synth_kernel(const float* __restrict__ bank_pp, int U, int K, const BasTe
 __global__ void __launch_bounds__(kThreads)
 bas_ir_synth_rows_kernel(const float* __restrict__ bank_pp, int U, int K, int pitch, long long n_points,
                          const BasTermDev* __restrict__ terms, float2* __restrict__ out) {
+    bas_grid_launch_dependents();
+    bas_grid_dependency_wait();
     const int L = U * K;
     __shared__ int s_base[2 * kMaxTerms];        // float offset of the phase row inside the bank (both ears)
     __shared__ int s_adv[2 * kMaxTerms];         // column advance a = ceil(shift / U)
@@ -116,6 +120,8 @@ bas_ir_synth_rows_kernel(const float* __restrict__ bank_pp, int U, int K, int pi
 __global__ void __launch_bounds__(kThreads)
 bas_ir_synth_full_kernel(const float* __restrict__ bank_pp, int U, int K, const BasTermDev* __restrict__ terms,
                          float* __restrict__ out, long long out_stride) {
+    bas_grid_launch_dependents();
+    bas_grid_dependency_wait();
     const long long point = blockIdx.y;
     const int ear = blockIdx.z;
     const int L = U * K;
@@ -154,15 +160,15 @@ extern "C" int bas_ir_synth(const float* bank_pp_dev, int U, int K, const bas_te
     const BasTermDev* terms = reinterpret_cast<const BasTermDev*>(terms_dev);
     if (mode == BAS_IR_ROWS) {
         BAS_CHECK_ARG((reinterpret_cast<uintptr_t>(out_dev) & 15) == 0, "filter rows must be 16-byte aligned");
-        bas_ir_synth_rows_kernel<<<(unsigned)n_points, kThreads, 0, st>>>(
-            bank_pp_dev, U, K, bas_filter_row_pitch(K), n_points, terms, reinterpret_cast<float2*>(out_dev));
+        BAS_CUDA(bas_launch(bas_ir_synth_rows_kernel, dim3((unsigned)n_points), dim3(kThreads), 0, st,
+                            bank_pp_dev, U, K, bas_filter_row_pitch(K), n_points, terms, reinterpret_cast<float2*>(out_dev)));
     } else if (mode == BAS_IR_PLANAR) {
         dim3 grid((unsigned)n_points, 2);
-        bas_ir_synth_kernel<<<grid, kThreads, 0, st>>>(bank_pp_dev, U, K, terms, out_dev, out_stride);
+        BAS_CUDA(bas_launch(bas_ir_synth_kernel, grid, dim3(kThreads), 0, st, bank_pp_dev, U, K, terms, out_dev, out_stride));
     } else {
         BAS_CHECK_ARG(n_points <= 65535, "n_points <= 65535 when mode is BAS_IR_UPSAMPLED");
         dim3 grid((unsigned)bas_ceil_div(out_stride, kThreads), (unsigned)n_points, 2);
-        bas_ir_synth_full_kernel<<<grid, kThreads, 0, st>>>(bank_pp_dev, U, K, terms, out_dev, out_stride);
+        BAS_CUDA(bas_launch(bas_ir_synth_full_kernel, grid, dim3(kThreads), 0, st, bank_pp_dev, U, K, terms, out_dev, out_stride));
     }
     BAS_LAUNCH_CHECK();
     return 0;

@@ -167,12 +167,12 @@ extern "C" int bas_pipeline_phase(const bas_pipeline_job* j, int phase, int n_ph
     float* out = reinterpret_cast<float*>(arena + l.out);
     float* peaks = reinterpret_cast<float*>(small + 2);
     const long long m = pt_end - pt_begin;
+    const bool fused = j->bank_pp2_dev != nullptr && bas_render_fused_supported(j->C, j->S) && (j->variant & 0x3f) != BAS_RENDER_GENERIC;
     mark("phase %lld called", phase, 0, nullptr, true);
 
-    if (phase == 0) {                   // status {0, INT-ish max} and zero peaks
+    if (phase == 0) {                   // status words and peaks: all zero
         BAS_CUDA(cudaMemsetAsync(small, 0, (size_t)(2 + j->n_src) * 4, mainst));
-        BAS_CUDA(cudaMemsetAsync(small + 1, 0x7f, 4, mainst));
-        mark("phase %lld memsets", phase, 0, mainst);
+        mark("phase %lld memset", phase, 0, mainst);
     }
     // directions of this phase -> plan -> filter rows.  With one az kind for all directions (the usual
     // case) they travel inside the plan launches themselves (bas_plan_build_inline); a host -> device
@@ -196,7 +196,8 @@ extern "C" int bas_pipeline_phase(const bas_pipeline_job* j, int phase, int n_ph
                                                    j->dirs_host + l.n_dirs + first, j->az_kind_all, m, t, small, first, mainst)) return rc;
             }
             if (s == 0) mark("phase %lld plan of source 0", phase, 0, mainst);
-            if (int rc = bas_ir_synth(j->bank_pp_dev, j->U, j->K, t, m, BAS_IR_ROWS, filt + first * l.pitch * 2, j->K, mainst)) return rc;
+            if (!fused)
+                if (int rc = bas_ir_synth(j->bank_pp_dev, j->U, j->K, t, m, BAS_IR_ROWS, filt + first * l.pitch * 2, j->K, mainst)) return rc;
         }
     }
     mark("phase %lld filter rows", phase, 0, mainst);
@@ -213,9 +214,13 @@ extern "C" int bas_pipeline_phase(const bas_pipeline_job* j, int phase, int n_ph
         for (long long pa = p_from; pa < p_to;) {
             long long pb = pa / kSegAlign * kSegAlign + step;     // cuts on the tile grid
             if (pb > p_to) pb = p_to;
-            if (int rc = bas_render(x, j->n_in, j->n_in, j->n_src, j->n_in, j->C, j->S, j->K, filt, nullptr, pa, pb - pa,
-                                    out + (pa - j->p_begin), l.stride, j->mix, peaks, j->variant, j->workspace_dev,
-                                    j->workspace_bytes, mainst)) return rc;
+            if (fused) {
+                if (int rc = bas_render_fused(x, j->n_in, j->n_in, j->n_src, j->n_in, j->C, j->S, j->K, terms, j->bank_pp2_dev, j->U, nullptr,
+                                              pa, pb - pa, out + (pa - j->p_begin), l.stride, j->mix, peaks, j->variant, j->workspace_dev,
+                                              j->workspace_bytes, mainst)) return rc;
+            } else if (int rc = bas_render(x, j->n_in, j->n_in, j->n_src, j->n_in, j->C, j->S, j->K, filt, nullptr, pa, pb - pa,
+                                           out + (pa - j->p_begin), l.stride, j->mix, peaks, j->variant, j->workspace_dev,
+                                           j->workspace_bytes, mainst)) return rc;
             BAS_CUDA(cudaEventRecord(ev->segment, mainst));
             BAS_CUDA(cudaStreamWaitEvent(down, ev->segment, 0));
             mark("render [%lld, %lld)", pa, pb, mainst);

@@ -19,16 +19,18 @@ static_assert(BAS_MAX_TERMS == 16 && BAS_N_DIR == BAS_N_DIRECTIONS, "constants")
 // One thread per (trajectory point, ear): the ear-independent ring lookups are recomputed by both
 // threads of a point (cheap) so that all 2*n_points threads run independently; 64-thread CTAs spread
 // a 5169-point trajectory over every SM.
-// status[0]: OR of the error bits of every point; status[1]: min over failing points of
-// (index << 3 | error bits of that point, both ears) - the reference raises at the FIRST bad
+// status[0]: OR of the error bits of every point; status[1]: bitwise complement of the minimum over failing
+// points of (index << 3 | error bits of that point, both ears) - the reference raises at the FIRST bad
 // trajectory point (apply_hrtf.py:429/:435 call interpolate_2d in time order), so the host needs the
-// bits of the earliest one.  The two ear threads of a point are neighbouring lanes.
+// bits of the earliest one.  Stored complemented (atomicMax) so that ALL-ZERO words mean "no error" and
+// one memset clears the status together with the peaks that follow it.  The two ear threads of a point
+// are neighbouring lanes.
 __device__ __forceinline__ void report_error(int* __restrict__ status, int err, long long idx) {
     const int both = err | __shfl_xor_sync(__activemask(), err, 1);
     if (both && status) {
         atomicOr(status, both);
         const long long capped = idx > BAS_STATUS_MAX_INDEX ? BAS_STATUS_MAX_INDEX : idx;
-        atomicMin(status + 1, (int)(capped << 3 | (both & 7)));
+        atomicMax(reinterpret_cast<unsigned*>(status) + 1, ~(unsigned)(capped << 3 | (both & 7)));
     }
 }
 
@@ -67,6 +69,8 @@ bas_plan_kernel(const double* __restrict__ diffs_l, const double* __restrict__ d
                 const uint8_t* __restrict__ az_kind, int az_kind_all, long long n_points,
                 BasTerm* __restrict__ terms, BasTrace* __restrict__ trace, int* __restrict__ status,
                 long long point_offset) {
+    bas_grid_launch_dependents();
+    bas_grid_dependency_wait();
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long p = t >> 1;
     if (p >= n_points) return;
@@ -85,6 +89,8 @@ __global__ void __launch_bounds__(64)
 bas_plan_inline_kernel(const __grid_constant__ InlineDirs dirs, const double* __restrict__ diffs_l,
                        const double* __restrict__ diffs_r, int U, long long L, int az_kind_all, int n_points,
                        BasTerm* __restrict__ terms, int* __restrict__ status, long long point_offset) {
+    bas_grid_launch_dependents();
+    bas_grid_dependency_wait();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int p = t >> 1;
     if (p >= n_points) return;
@@ -104,17 +110,14 @@ int bas_plan_build_range(const double* diffs_left_dev, const double* diffs_right
     if (n_points == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (status_dev && reset_status) {
-        // {0, 0x7f7f7f7f}: memsets keep the call capturable in a CUDA graph
-        BAS_CUDA(cudaMemsetAsync(status_dev, 0, sizeof(int), st));
-        BAS_CUDA(cudaMemsetAsync(status_dev + 1, 0x7f, sizeof(int), st));
+        BAS_CUDA(cudaMemsetAsync(status_dev, 0, 2 * sizeof(int), st));     // a memset keeps the call capturable in a CUDA graph
     }
     const int threads = 64;
     const long long blocks = bas_ceil_div(2 * n_points, threads);
     BAS_CHECK_ARG(blocks < 0x7fffffffLL, "too many points for one launch");
-    bas_plan_kernel<<<(unsigned)blocks, threads, 0, st>>>(
-        diffs_left_dev, diffs_right_dev, U, (long long)L, elev_dev, azim_dev, az_kind_dev, az_kind_all, n_points,
-        reinterpret_cast<BasTerm*>(terms_dev), reinterpret_cast<BasTrace*>(trace_dev), status_dev, point_offset);
-    BAS_LAUNCH_CHECK();
+    BAS_CUDA(bas_launch(bas_plan_kernel, dim3((unsigned)blocks), dim3(threads), 0, st,
+                        diffs_left_dev, diffs_right_dev, U, (long long)L, elev_dev, azim_dev, az_kind_dev, az_kind_all, n_points,
+                        reinterpret_cast<BasTerm*>(terms_dev), reinterpret_cast<BasTrace*>(trace_dev), status_dev, point_offset));
     return 0;
 }
 
@@ -218,10 +221,7 @@ extern "C" int bas_plan_ring(const double* diffs_left_dev, const double* diffs_r
     BAS_CHECK_ARG(n >= 0 && n < 0x3fffffffLL, "n");
     if (n == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (status_dev) {
-        BAS_CUDA(cudaMemsetAsync(status_dev, 0, sizeof(int), st));
-        BAS_CUDA(cudaMemsetAsync(status_dev + 1, 0x7f, sizeof(int), st));
-    }
+    if (status_dev) BAS_CUDA(cudaMemsetAsync(status_dev, 0, 2 * sizeof(int), st));
     bas_plan_ring_kernel<<<(unsigned)bas_ceil_div(2 * n, 64), 64, 0, st>>>(diffs_left_dev, diffs_right_dev, U, (long long)L, rows_dev, weights_dev,
                                                                          n, reinterpret_cast<BasTerm*>(terms_dev), delays_dev, status_dev);
     BAS_LAUNCH_CHECK();

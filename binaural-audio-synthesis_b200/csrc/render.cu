@@ -52,6 +52,8 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 bas_render_generic_kernel(RenderParams prm) {
+    bas_grid_launch_dependents();
+    bas_grid_dependency_wait();
     const long long p = prm.p_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = p < prm.p_end;
     const int s_first = prm.mix ? 0 : blockIdx.y;
@@ -102,6 +104,8 @@ bas_render_generic_kernel(RenderParams prm) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 bas_peak_kernel(const float* __restrict__ v, long long n, float* __restrict__ peak) {
+    bas_grid_launch_dependents();
+    bas_grid_dependency_wait();
     float m = 0.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         m = fmaxf(m, fabsf(v[i]));
@@ -111,6 +115,8 @@ bas_peak_kernel(const float* __restrict__ v, long long n, float* __restrict__ pe
 
 __global__ void __launch_bounds__(256)
 bas_normalise_kernel(float* __restrict__ v, long long n, const float* __restrict__ peak) {
+    bas_grid_launch_dependents();
+    bas_grid_dependency_wait();
     const float m = *peak;
     if (!(m > 1.f)) return;                      // apply_hrtf.py:463: only when the peak exceeds 1
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -121,11 +127,14 @@ bas_normalise_kernel(float* __restrict__ v, long long n, const float* __restrict
 
 // variant encoding beyond the public ones: BAS_RENDER_TILED | (TW << 8) | (NS << 16) requests a tile
 // shape (tuning sweeps; unknown shapes return BAS_E_UNSUPPORTED).
-extern "C" int bas_render(const float* x_dev, long long x_stride, long long n_valid, int n_src, long long n_in,
-                          int C, int S, int K, const float* filt_dev, const float* gains_dev,
-                          long long p_begin, long long p_count, float* out_dev, long long out_stride, int mix,
-                          float* peaks_dev, int variant, void* workspace_dev, long long workspace_bytes, void* stream) {
-    BAS_CHECK_ARG(x_dev && filt_dev && out_dev, "null pointer");
+// filt_dev: filter rows written by bas_ir_synth(BAS_IR_ROWS); or, fused, terms_dev + bank_pp2_dev + U: the
+// tiled kernel synthesises the rows itself.
+static int render_common(const float* x_dev, long long x_stride, long long n_valid, int n_src, long long n_in,
+                         int C, int S, int K, const float* filt_dev, const bas_term* terms_dev, const float* bank_pp2_dev, int U,
+                         const float* gains_dev, long long p_begin, long long p_count, float* out_dev, long long out_stride, int mix,
+                         float* peaks_dev, int variant, void* workspace_dev, long long workspace_bytes, void* stream) {
+    const bool fused = filt_dev == nullptr;
+    BAS_CHECK_ARG(x_dev && out_dev && (filt_dev || (terms_dev && bank_pp2_dev && U >= 1)), "null pointer");
     BAS_CHECK_ARG(n_src >= 1, "n_src");
     BAS_CHECK_ARG(mix == 0 || mix == 1 || mix == BAS_MIX_ACCUMULATE, "mix must be 0, 1 or BAS_MIX_ACCUMULATE");
     BAS_CHECK_ARG(C >= 1 && S >= 1 && C % S == 0, "subchunksize must divide chunksize");     // apply_hrtf.py:401-402
@@ -144,12 +153,13 @@ extern "C" int bas_render(const float* x_dev, long long x_stride, long long n_va
     prm.filt_src_stride = (n_in / C + 1) * (long long)prm.pitch;
     prm.gains = gains_dev; prm.p_begin = p_begin; prm.p_end = p_begin + p_count;
     prm.out = out_dev; prm.out_stride = out_stride; prm.mix = mix ? 1 : 0; prm.accumulate = mix == BAS_MIX_ACCUMULATE ? 1 : 0; prm.peaks = peaks_dev; prm.tiles = 0; prm.parts = 1; prm.tmap = 0; prm.box_rows = 0; prm.n_box = 0;
+    prm.terms = reinterpret_cast<const TermDev*>(terms_dev); prm.bank2 = bank_pp2_dev; prm.U = U;
 
     const int base = variant & 0x3f;
     BAS_CHECK_ARG(base == BAS_RENDER_AUTO || base == BAS_RENDER_GENERIC || base == BAS_RENDER_TILED, "variant");
     const bool tiled_ok = S == kBlk && C % kBlk == 0 && n_valid % 4 == 0 && (reinterpret_cast<uintptr_t>(x_dev) & 15) == 0 &&
-                          (reinterpret_cast<uintptr_t>(filt_dev) & 15) == 0 && (n_src == 1 || x_stride % 4 == 0);
-    if (base == BAS_RENDER_TILED && !tiled_ok) {
+                          (fused || (reinterpret_cast<uintptr_t>(filt_dev) & 15) == 0) && (n_src == 1 || x_stride % 4 == 0);
+    if ((base == BAS_RENDER_TILED || fused) && !tiled_ok) {
         bas_set_error("bas_render: tiled kernel needs S == 32, 32 | C, 4 | n_valid, 16-byte aligned signals and filter rows");
         return BAS_E_UNSUPPORTED;
     }
@@ -159,7 +169,7 @@ extern "C" int bas_render(const float* x_dev, long long x_stride, long long n_va
         // 28..30 parts (code n: 2^(n-1)); otherwise the shape with the lowest estimated time is taken.
         const int tw_req = (variant >> 8) & 0xff, ns_req = (variant >> 16) & 0xff, cta_req = (variant >> 24) & 0xf;
         const int parts_code = (variant >> 28) & 0x7, parts_req = parts_code ? 1 << (parts_code - 1) : 0;
-        const int mixi = prm.mix ? 1 : 0;
+        const int mixi = (prm.mix ? 1 : 0) + (fused ? 2 : 0);
         const int D = (K + kBlk - 1) / kBlk;
         const long long p_base = p_begin / kBlk * kBlk;
         const bool split = (variant & BAS_RENDER_SPLIT) || (prm.mix && !(variant & BAS_RENDER_NO_SPLIT));
@@ -210,13 +220,40 @@ extern "C" int bas_render(const float* x_dev, long long x_stride, long long n_va
             return rc;
         }
     }
+    if (fused) { bas_set_error("bas_render_fused: no tile shape fits K=%d C=%d", K, C); return BAS_E_UNSUPPORTED; }
     const int threads = 256;
     const long long blocks = bas_ceil_div(p_count, threads);
     BAS_CHECK_ARG(blocks < 0x7fffffffLL && n_src <= 65535, "launch too large");
     dim3 grid((unsigned)blocks, prm.mix ? 1u : (unsigned)n_src);
-    bas_render_generic_kernel<<<grid, threads, 0, st>>>(prm);
-    BAS_LAUNCH_CHECK();
+    cudaError_t e = bas_launch(bas_render_generic_kernel, grid, dim3(threads), 0, st, prm);
+    if (e != cudaSuccess) { bas_set_error("bas_render: generic launch failed: %s", cudaGetErrorString(e)); return (int)e; }
     return 0;
+}
+
+extern "C" int bas_render(const float* x_dev, long long x_stride, long long n_valid, int n_src, long long n_in,
+                          int C, int S, int K, const float* filt_dev, const float* gains_dev,
+                          long long p_begin, long long p_count, float* out_dev, long long out_stride, int mix,
+                          float* peaks_dev, int variant, void* workspace_dev, long long workspace_bytes, void* stream) {
+    BAS_CHECK_ARG(filt_dev, "null pointer");
+    return render_common(x_dev, x_stride, n_valid, n_src, n_in, C, S, K, filt_dev, nullptr, nullptr, 0, gains_dev, p_begin, p_count,
+                         out_dev, out_stride, mix, peaks_dev, variant, workspace_dev, workspace_bytes, stream);
+}
+
+extern "C" int bas_render_fused(const float* x_dev, long long x_stride, long long n_valid, int n_src, long long n_in,
+                                int C, int S, int K, const bas_term* terms_dev, const float* bank_pp2_dev, int U,
+                                const float* gains_dev, long long p_begin, long long p_count, float* out_dev, long long out_stride,
+                                int mix, float* peaks_dev, int variant, void* workspace_dev, long long workspace_bytes, void* stream) {
+    BAS_CHECK_ARG(terms_dev && bank_pp2_dev, "null pointer");
+    BAS_CHECK_ARG(U >= 1 && (long long)U * K < (1 << 20) && (2LL * BAS_N_DIRECTIONS * U * 2 * K) < 0x7fffffffLL, "U");
+    return render_common(x_dev, x_stride, n_valid, n_src, n_in, C, S, K, nullptr, terms_dev, bank_pp2_dev, U, gains_dev, p_begin, p_count,
+                         out_dev, out_stride, mix, peaks_dev, variant, workspace_dev, workspace_bytes, stream);
+}
+
+extern "C" int bas_render_fused_supported(int C, int S) { return S == kBlk && C % kBlk == 0 ? 1 : 0; }
+
+extern "C" long long bas_bank2_floats(int U, int K) {
+    // every phase row twice + padding for the second tap of a gather pass (render_tiled.cuh)
+    return U < 1 || K < 1 ? BAS_E_ARG : 2LL * BAS_N_DIRECTIONS * U * 2 * K + 1024;
 }
 
 namespace bas_render_detail {
@@ -278,8 +315,8 @@ extern "C" int bas_peak(const float* v_dev, long long n, float* peak_dev, void* 
     BAS_CHECK_ARG(v_dev && peak_dev && n >= 0, "bad pointer or size");
     if (n == 0) return 0;
     const long long blocks = bas_ceil_div(n, 256 * 8);
-    bas_peak_kernel<<<(unsigned)(blocks > 148 * 8 ? 148 * 8 : blocks), 256, 0, (cudaStream_t)stream>>>(v_dev, n, peak_dev);
-    BAS_LAUNCH_CHECK();
+    BAS_CUDA(bas_launch(bas_peak_kernel, dim3((unsigned)(blocks > 148 * 8 ? 148 * 8 : blocks)), dim3(256), 0, (cudaStream_t)stream,
+                        v_dev, n, peak_dev));
     return 0;
 }
 
@@ -287,7 +324,7 @@ extern "C" int bas_normalise(float* out_dev, long long n, const float* peak_dev,
     BAS_CHECK_ARG(out_dev && peak_dev && n >= 0, "bad pointer or size");
     if (n == 0) return 0;
     const long long blocks = bas_ceil_div(n, 256 * 8);
-    bas_normalise_kernel<<<(unsigned)(blocks > 148 * 8 ? 148 * 8 : blocks), 256, 0, (cudaStream_t)stream>>>(out_dev, n, peak_dev);
-    BAS_LAUNCH_CHECK();
+    BAS_CUDA(bas_launch(bas_normalise_kernel, dim3((unsigned)(blocks > 148 * 8 ? 148 * 8 : blocks)), dim3(256), 0, (cudaStream_t)stream,
+                        out_dev, n, peak_dev));
     return 0;
 }

@@ -7,6 +7,8 @@
 
 namespace bas_render_detail {
 
+struct TermDev { int32_t row_shift; float weight; };      // bas_term
+
 struct RenderParams {
     const float* x; long long x_stride; long long n_valid;
     int n_src; long long n_in;
@@ -24,6 +26,11 @@ struct RenderParams {
     int parts;                     // tiled kernel: warps that share one 1024-output stripe (split along the taps)
     int tmap;                      // tiled kernel: input rows arrive by tensor-map TMA (128-byte swizzle), else bulk copy + re-layout
     int box_rows, n_box;           // tensor-map path: rows per copy, copies per item
+    // fused filter synthesis (FUSED kernels): the filter rows of an item are not copied from `filt` but
+    // synthesised by the CTA itself from the plan terms and the L2-resident polyphase bank
+    const TermDev* terms;          // [n_src][n_in/C + 1][2 ears][16] (bas_plan_build)
+    const float* bank2;            // polyphase bank with every phase row stored twice: [ear][row][U][2K] (+ padding)
+    int U;
 };
 
 __device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
@@ -157,10 +164,11 @@ __host__ __device__ inline size_t tmap_stage_bytes(const TileGeom& g) {
     const size_t x = (size_t)tmap_n_box(g.x_rows) * tmap_box_rows(g.x_rows) * 128;
     return (x + g.f_bytes + 1023) / 1024 * 1024;                  // every stage starts on a swizzle atom
 }
-__host__ __device__ inline size_t tile_smem_bytes(const TileGeom& g, int TW, int NS, int parts, int C, bool mix, bool tmap) {
+constexpr int kTermsPerRow = 2 * BAS_MAX_TERMS;             // both ears
+__host__ __device__ inline size_t tile_smem_bytes(const TileGeom& g, int TW, int NS, int parts, int C, bool mix, bool tmap, bool fused = false) {
     const int TS = TW / parts;
     const size_t staging = tmap ? 1024 + (size_t)NS * tmap_stage_bytes(g) : (size_t)NS * g.stage_bytes + (size_t)TW * g.warp_x_bytes;
-    return kBarBytes + staging + (size_t)((C / kBlk * 4 + 15) / 16 * 16) +
+    return kBarBytes + staging + (size_t)((C / kBlk * 4 + 15) / 16 * 16) + (fused ? (size_t)g.f_rows * kTermsPerRow * 8 : 0) +
            (parts > 1 ? (size_t)(TW - TS) * kStripeBytes : 0) + (mix ? (size_t)TS * kStripeBytes : 0);
 }
 
@@ -273,7 +281,12 @@ __device__ __forceinline__ void cta_barrier(int threads) {
 // the item's tap blocks; their partial sums meet in shared memory in a fixed order.  A tile is then
 // TW / parts stripes: smaller tiles and more of them, which is what fills the last wave of a launch
 // whose tile count is a small multiple of the resident warps.
-template <int TW, bool MIX, int NS, int MINB>
+// FUSED: the boundary-filter rows an item needs are synthesised by the CTA's own warps straight into the
+// stage (interpolate_2d's array part, apply_hrtf.py:219-281, = ir_synth.cu's weighted gather) instead of being
+// copied from a filter-row array that a separate bas_ir_synth launch wrote: the gathers lean on L2 while the FMA
+// pipe idles, the FIR blocks are the exact complement, and with two or three CTAs per SM one CTA's gather
+// phase hides under its neighbours' FMA phase.  Same terms, same order of summation: bit-identical rows.
+template <int TW, bool MIX, int NS, int MINB, bool FUSED = false>
 __global__ void __launch_bounds__(TW * 32, MINB)
 bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ workspace, const __grid_constant__ CUtensorMap xmap) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -294,7 +307,9 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
     unsigned char* after_stages = stage_base + (size_t)NS * stage_stride;
     float* xw = reinterpret_cast<float*>(after_stages + (size_t)warp * g.warp_x_bytes);          // unused on the tensor-map path
     float* alpha_tab = reinterpret_cast<float*>(after_stages + (tmap ? 0 : (size_t)TW * g.warp_x_bytes));
-    unsigned char* after_alpha = reinterpret_cast<unsigned char*>(alpha_tab) + (spc * 4 + 15) / 16 * 16;
+    unsigned char* after_tab = reinterpret_cast<unsigned char*>(alpha_tab) + (spc * 4 + 15) / 16 * 16;
+    int2* term_tab = reinterpret_cast<int2*>(after_tab);     // FUSED: {float offset into bank2, weight bits} per (row, ear, slot)
+    unsigned char* after_alpha = after_tab + (FUSED ? (size_t)g.f_rows * kTermsPerRow * 8 : 0);
     // partial sums of parts 1..P-1 of every stripe: [stripe][part - 1][r][lane] {L,R}
     u64* red = reinterpret_cast<u64*>(after_alpha);
     u64* mixbuf = reinterpret_cast<u64*>(after_alpha + (P > 1 ? (size_t)(TW - TS) * kStripeBytes : 0)) + (size_t)stripe * kWarpTile;
@@ -316,6 +331,10 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
     }
     for (int s = tid; s < spc; s += TW * 32) alpha_tab[s] = (float)(s * kBlk) / (float)prm.C;      // apply_hrtf.py:442
     __syncthreads();
+    // programmatic dependent launch: everything above overlapped the tail of the previous kernel in the
+    // stream; the filter rows / plan terms it wrote are read only from here on
+    bas_grid_launch_dependents();
+    bas_grid_dependency_wait();
 
     // item j of this CTA (32-bit arithmetic: the host keeps slice counts below 2^31)
     auto item_info = [&](int j) {
@@ -379,7 +398,7 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
             float* xs = reinterpret_cast<float*>(stage_base + (size_t)st * stage_stride);
             float2* fs = reinterpret_cast<float2*>(stage_base + (size_t)st * stage_stride + x_stage_bytes);
             const float* x = prm.x + (long long)it.src * prm.x_stride;
-            const unsigned f_bytes = (unsigned)n_rows * prm.pitch * 8;
+            const unsigned f_bytes = FUSED ? 0u : (unsigned)n_rows * prm.pitch * 8;
             if (tmap) {
                 // input rows: n_box tiled copies of box_rows rows each (rows outside the signal are zero-filled by
                 // the TMA unit, and count towards the transaction bytes); filter rows: one bulk copy
@@ -397,16 +416,13 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
                 mbar_arrive_expect_tx(full_bar + st, x_bytes + f_bytes);
                 if (x_bytes) bulk_g2s(xs + (na - n_lo), x + na, x_bytes, full_bar + st);
             }
-            bulk_g2s(fs, prm.filt + (long long)it.src * prm.filt_src_stride + c_first * prm.pitch, f_bytes, full_bar + st);
+            if (!FUSED) bulk_g2s(fs, prm.filt + (long long)it.src * prm.filt_src_stride + c_first * prm.pitch, f_bytes, full_bar + st);
         }
         __syncwarp();
     };
 
     if (warp == 0 && n_items > 0) produce(0);
 
-    u64 acc[kBlk];
-#pragma unroll
-    for (int r = 0; r < kBlk; ++r) acc[r] = 0ull;
     if (MIX && part == 0) {
 #pragma unroll
         for (int r = 0; r < kBlk; ++r) mixbuf[r * 32 + lane] = 0ull;
@@ -431,6 +447,58 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
         // this warp's share of the item's tap blocks
         const int len = it.d1 - it.d0;
         const int d_first = it.d0 + (len * part) / P, d_last = it.d0 + (len * (part + 1)) / P;
+
+        if (FUSED) {
+            // ---- filter rows of this item: out[m] = sum_t w_t * bank[row_t][phase_t][(m - adv_t) mod K] per ear, the
+            //      terms in their fixed plan slots (a slot with weight zero reads column m of the bank's first
+            //      phase row with weight zero: adds exactly nothing), summed in slot order like ir_synth.cu.
+            //      Every phase row is stored twice in a row, so (m - adv) mod K is the plain index m + K - adv.
+            cta_barrier(TW * 32);                           // every warp has left the previous item's rows and table
+            const TermDev* tsrc = prm.terms + ((long long)it.src * (n_chunks + 1) + c_first) * kTermsPerRow;
+            const int K2 = 2 * prm.K;
+            for (int e = tid; e < n_rows * kTermsPerRow; e += TW * 32) {
+                const TermDev t = tsrc[e];
+                const int ear = (e & (kTermsPerRow - 1)) / BAS_MAX_TERMS;
+                const int row = t.row_shift >> 20, shift = t.row_shift & 0xFFFFF;
+                const int ph = (prm.U - shift % prm.U) % prm.U;
+                const int adv = (shift + ph) / prm.U;
+                const int off = t.weight != 0.f ? ((ear * BAS_N_DIRECTIONS + row) * prm.U + ph) * K2 + prm.K - adv : 0;
+                term_tab[e] = make_int2(off, __float_as_int(t.weight));
+            }
+            cta_barrier(TW * 32);
+            float2* fsw = reinterpret_cast<float2*>(stage_base + (size_t)st * stage_stride + x_stage_bytes);
+            constexpr int T = TW * 32;
+            for (int r = 0; r < n_rows; ++r) {
+                const int2* tab = term_tab + r * kTermsPerRow;
+                float2* dst = fsw + r * prm.pitch;
+                // two taps per thread and pass (m, m + T): one table read serves both, the second load is the
+                // first address plus a constant (the bank carries padding, so it is always in bounds)
+                for (int m = tid; m < prm.K; m += 2 * T) {
+                    const float* b0 = prm.bank2 + m;
+                    float v0[kTermsPerRow], v1[kTermsPerRow];
+#pragma unroll
+                    for (int t = 0; t < kTermsPerRow; ++t) {
+                        const int off = tab[t].x;
+                        v0[t] = __ldg(b0 + off);
+                        v1[t] = __ldg(b0 + off + T);
+                    }
+                    float l0 = 0.f, r0 = 0.f, l1 = 0.f, r1 = 0.f;
+#pragma unroll
+                    for (int t = 0; t < BAS_MAX_TERMS; ++t) {
+                        const float wl = __int_as_float(tab[t].y), wr = __int_as_float(tab[BAS_MAX_TERMS + t].y);
+                        l0 = fmaf(wl, v0[t], l0); r0 = fmaf(wr, v0[BAS_MAX_TERMS + t], r0);
+                        l1 = fmaf(wl, v1[t], l1); r1 = fmaf(wr, v1[BAS_MAX_TERMS + t], r1);
+                    }
+                    dst[m] = make_float2(l0, r0);
+                    if (m + T < prm.K) dst[m + T] = make_float2(l1, r1);
+                }
+                for (int m = prm.K + tid; m < prm.pitch; m += T) dst[m] = make_float2(0.f, 0.f);     // zero padding taps
+            }
+            cta_barrier(TW * 32);
+        }
+        u64 acc[kBlk];
+#pragma unroll
+        for (int r = 0; r < kBlk; ++r) acc[r] = 0ull;
 
         mbar_wait(full_bar + st, (unsigned)((j / NS) & 1));
 
@@ -632,20 +700,20 @@ inline int device_sm_count() {
 }
 
 // Resident CTAs per SM this shape reaches with `parts` warps per stripe (0: does not fit).
-template <int TW, bool MIX, int NS, int MINB>
+template <int TW, bool MIX, int NS, int MINB, bool FUSED>
 int tiled_ctas_per_sm(int K, int C, int pitch, int parts, bool tmap) {
     if (parts < 1 || TW % parts) return 0;
     const TileGeom g = tile_geom(K, C, pitch, TW / parts);
-    const size_t smem = tile_smem_bytes(g, TW, NS, parts, C, MIX, tmap);
+    const size_t smem = tile_smem_bytes(g, TW, NS, parts, C, MIX, tmap, FUSED);
     if (smem > 227 * 1024) return 0;
-    auto kern = bas_render_tiled_kernel<TW, MIX, NS, MINB>;
+    auto kern = bas_render_tiled_kernel<TW, MIX, NS, MINB, FUSED>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TW * 32, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
     return per_sm;
 }
 
-template <int TW, bool MIX, int NS, int MINB>
+template <int TW, bool MIX, int NS, int MINB, bool FUSED>
 int launch_tiled(RenderParams prm, int parts, bool want_split, float* workspace, long long workspace_bytes, cudaStream_t st) {
     if (parts < 1 || TW % parts) return BAS_E_UNSUPPORTED;
     const int TS = TW / parts;
@@ -656,9 +724,9 @@ int launch_tiled(RenderParams prm, int parts, bool want_split, float* workspace,
     prm.n_box = tmap_n_box(g.x_rows);
     prm.box_rows = tmap_box_rows(g.x_rows);
     prm.tmap = make_input_tensor_map(&xmap, prm, prm.box_rows) ? 1 : 0;
-    const size_t smem = tile_smem_bytes(g, TW, NS, parts, prm.C, MIX, prm.tmap != 0);
+    const size_t smem = tile_smem_bytes(g, TW, NS, parts, prm.C, MIX, prm.tmap != 0, FUSED);
     if (smem > 227 * 1024) return BAS_E_UNSUPPORTED;
-    auto kern = bas_render_tiled_kernel<TW, MIX, NS, MINB>;
+    auto kern = bas_render_tiled_kernel<TW, MIX, NS, MINB, FUSED>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { bas_set_error("bas_render: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     const long long p_base = prm.p_begin / kBlk * kBlk;
@@ -683,23 +751,24 @@ int launch_tiled(RenderParams prm, int parts, bool want_split, float* workspace,
     const long long need = (long long)ws_bytes(grid, TS);
     sp.split = (want_split && workspace && workspace_bytes >= need && grid > 1 && sp.total / grid >= sp.gs + 1) ? 1 : 0;
     sp.epoch = sp.split ? next_epoch() : 0ull;
-    kern<<<(unsigned)grid, TW * 32, smem, st>>>(prm, sp, workspace, xmap);
-    e = cudaGetLastError();
+    e = bas_launch(kern, dim3((unsigned)grid), dim3(TW * 32), smem, st, prm, sp, workspace, xmap);
     if (e != cudaSuccess) { bas_set_error("bas_render: tiled launch failed: %s", cudaGetErrorString(e)); return (int)e; }
     return 0;
 }
 
 // One compiled tile shape: warps per CTA x pipeline stages x CTAs per SM the registers allow.
-// [0] = one source per tile, [1] = mixing.
+// index = mix + 2 * fused: [0] one source per tile, [1] mixing, [2] / [3] the same with fused filter synthesis.
 struct TiledShape {
     int tw, ns, minb;
-    int (*ctas_per_sm[2])(int K, int C, int pitch, int parts, bool tmap);
-    int (*launch[2])(RenderParams prm, int parts, bool want_split, float* workspace, long long workspace_bytes, cudaStream_t st);
+    int (*ctas_per_sm[4])(int K, int C, int pitch, int parts, bool tmap);
+    int (*launch[4])(RenderParams prm, int parts, bool want_split, float* workspace, long long workspace_bytes, cudaStream_t st);
 };
-#define BAS_TILED_SHAPE(TW_, NS_, MINB_)                                                            \
-    { TW_, NS_, MINB_,                                                                              \
-      { tiled_ctas_per_sm<TW_, false, NS_, MINB_>, tiled_ctas_per_sm<TW_, true, NS_, MINB_> },      \
-      { launch_tiled<TW_, false, NS_, MINB_>, launch_tiled<TW_, true, NS_, MINB_> } }
+#define BAS_TILED_SHAPE(TW_, NS_, MINB_)                                                                       \
+    { TW_, NS_, MINB_,                                                                                         \
+      { tiled_ctas_per_sm<TW_, false, NS_, MINB_, false>, tiled_ctas_per_sm<TW_, true, NS_, MINB_, false>,     \
+        tiled_ctas_per_sm<TW_, false, NS_, MINB_, true>, tiled_ctas_per_sm<TW_, true, NS_, MINB_, true> },     \
+      { launch_tiled<TW_, false, NS_, MINB_, false>, launch_tiled<TW_, true, NS_, MINB_, false>,               \
+        launch_tiled<TW_, false, NS_, MINB_, true>, launch_tiled<TW_, true, NS_, MINB_, true> } }
 
 // defined in render_tw4.cu / render_tw6.cu / render_tw8.cu (one translation unit per tile width, so
 // they compile in parallel)

@@ -3,13 +3,16 @@
 The reference is single-process; SURVEY.md 8(e) identifies the two ways its hot path shards:
 
   by source   sources are independent calls of make_signal_move_2d (no cross-call state): every rank
-              renders and mixes its own sources, then one SUM reduce of the (2, N_out) fp32 mix over
-              NVLink.  No other exchange.
+              renders and mixes its own sources, and the (2, N_out) fp32 mixes are summed over
+              NVLink.  The sum is NOT one collective after the last render: the output is cut into
+              time segments, and while segment i+1 renders (FP32 pipe) segment i is already being
+              reduced (NCCL on its own stream, NVSwitch), so only the last segment's reduction is
+              exposed.  Host signals are uploaded time slice by time slice under the same loop.
   by time     given the trajectory, chunks are independent except for the K-1 sample FIR tail
               (apply_hrtf.py:450-453).  The signal is cut at multiples of `chunksize`; each rank
               renders the OUTPUT samples of its segment from its inputs plus a K-1 sample input halo
-              (output-stationary: no tail exchange), and one MAX all-reduce of the peak implements
-              the global normalisation (apply_hrtf.py:462-464).
+              (output-stationary: no tail exchange), one MAX all-reduce of the peak implements the
+              global normalisation (apply_hrtf.py:462-464), and an all-gather assembles the result.
 
 `local_render` is injectable so the partition / halo / collective logic can be exercised on CPU
 ranks (gloo) in tests; the default is the CUDA path and there is no CPU fallback in the product.
@@ -17,6 +20,9 @@ ranks (gloo) in tests; the default is the CUDA path and there is no CPU fallback
 from __future__ import annotations
 
 import numpy as np
+
+MIX_SEGMENTS = 6                 # time segments of a by-source mix (render i+1 overlaps the reduction of i)
+_SEGMENT_ALIGN = 8192            # output samples: whole render tiles for every tile width
 
 
 def shard_sources(n_src: int, rank: int, world: int):
@@ -44,20 +50,134 @@ def segment_inputs(p0: int, p1: int, n_in: int, chunksize: int, ir_length: int):
     return (n0, max(n1, n0 + chunksize))
 
 
+def mix_segments(n_out: int, n_segments: int = None):
+    """Cut [0, n_out) into about `n_segments` ranges on the render tile grid."""
+    n_segments = max(1, int(n_segments or MIX_SEGMENTS))
+    step = -(-n_out // n_segments)
+    step = (step + _SEGMENT_ALIGN - 1) // _SEGMENT_ALIGN * _SEGMENT_ALIGN
+    cuts = list(range(0, n_out, step)) + [n_out]
+    return list(zip(cuts[:-1], cuts[1:]))
+
+
 def _default_render(*args, **kwargs):
     from .apply_hrtf import render_sources
     return render_sources(*args, **kwargs)
 
 
 def render_mix_by_source(signals, chunksize, subchunksize, elev_azim_functions, bank, group=None,
-                         dst=None, local_render=None, normalise=True):
-    """Every rank passes ONLY its own sources (see shard_sources).  Returns the global mix
-    (2, N_out): on every rank (all_reduce) when dst is None, else only on rank `dst` (reduce; other
-    ranks get None).  The collective runs on the tensor the renderer produced (NCCL on CUDA
-    tensors, gloo on CPU tensors)."""
+                         dst=None, local_render=None, normalise=True, n_segments=None):
+    """Every rank passes ONLY its own sources (see shard_sources): an (n_local, N) array (host or CUDA)
+    and one trajectory per local source.  Returns the global mix (2, N_out): on every rank
+    (all_reduce) when dst is None, else only on rank `dst` (reduce; other ranks get None).  The sum
+    over a rank's own sources is deterministic; the sum over ranks is NCCL's."""
     import torch
     import torch.distributed as dist
-    render = local_render or _default_render
+    if local_render is not None:
+        return _render_mix_injected(torch, dist, signals, chunksize, subchunksize, elev_azim_functions, bank, group, dst,
+                                    local_render, normalise)
+    from . import apply_hrtf as ah
+    from ._cabi import lib, check, decode_status
+    torch_dev = torch.device('cuda', torch.cuda.current_device())
+    n_local = len(signals)
+    rank = dist.get_rank(group)
+    # every rank needs the geometry, also one without sources
+    n = int(signals.shape[1]) if n_local else 0
+    n_t = torch.tensor([n], dtype=torch.int64, device=torch_dev)
+    dist.all_reduce(n_t, op=dist.ReduceOp.MAX, group=group)
+    n = int(n_t)
+    k, n_in, n_out = ah.render_geometry(n, chunksize, subchunksize, bank)
+    stride = (n_out + 3) // 4 * 4
+    main = torch.cuda.current_stream()
+    mix = torch.zeros((2, stride), dtype=torch.float32, device=torch_dev)
+    segs = mix_segments(n_out, n_segments)
+    job = None
+    uploaded = {}
+    if n_local:
+        dev = ah._device_bank(bank)
+        up, _ = ah._streams(torch, torch_dev)
+        if isinstance(signals, torch.Tensor) and signals.is_cuda:
+            if signals.dtype == torch.float32 and signals.is_contiguous() and n == n_in:
+                x = signals
+            else:
+                x = torch.zeros((n_local, n_in), dtype=torch.float32, device=torch_dev)
+                x[:, :n].copy_(signals)
+        else:
+            # host signals: uploaded time slice by time slice on a side stream, each slice ahead of the
+            # segment that needs it (a segment [pa, pb) reads inputs below pb)
+            host = signals.numpy() if isinstance(signals, torch.Tensor) else signals
+            host = np.ascontiguousarray(host, dtype=np.float32)
+            ah._pin_in_place(host)
+            x = ah._scratch(torch, (n_local, n_in), torch.float32, torch_dev)
+            up.wait_stream(main)
+            if n_in > n:
+                with torch.cuda.stream(up):
+                    x[:, n:].zero_()                        # zero padding of apply_hrtf.py:405-406
+            lo = 0
+            for i, (pa, pb) in enumerate(segs):
+                hi = min(n, pb)
+                if hi > lo:
+                    check(lib.bas_copy_2d(x.data_ptr() + 4 * lo, 4 * n_in, host.ctypes.data + 4 * lo, 4 * n, 4 * (hi - lo), n_local, 1,
+                                          up.cuda_stream), 'bas_copy_2d')
+                    lo = hi
+                uploaded[i] = torch.cuda.Event()
+                uploaded[i].record(up)
+        elev, azim, kinds = ah._directions(elev_azim_functions, n_local, n_in, chunksize)
+        elev_d = torch.as_tensor(np.asarray(elev) if not isinstance(elev, torch.Tensor) else elev, dtype=torch.float64).to(torch_dev).contiguous()
+        azim_d = torch.as_tensor(np.asarray(azim) if not isinstance(azim, torch.Tensor) else azim, dtype=torch.float64).to(torch_dev).contiguous()
+        if elev_d.numel() != n_local * (n_in // chunksize + 1) or azim_d.numel() != elev_d.numel():
+            raise ValueError('trajectories must give %d directions per source' % (n_in // chunksize + 1))
+        job = ah.DeviceRender(torch, dev, x, n_in, chunksize, subchunksize, elev_d.reshape(-1), azim_d.reshape(-1), kinds, True,
+                              ah._cabi.RENDER_AUTO)
+        job.plan(main.cuda_stream)
+
+    def one_pass(gains):
+        works = []
+        for i, (pa, pb) in enumerate(segs):
+            if job is not None:
+                if i in uploaded:
+                    main.wait_event(uploaded[i])
+                job.render(main.cuda_stream, pa, pb, mix.data_ptr() + 4 * pa, stride, gains=gains)
+            # the collective is ordered after the render just enqueued and runs on NCCL's own stream:
+            # the next segment's render does not wait for it.  One call per ear row (contiguous slices).
+            for ear in range(2):
+                piece = mix[ear, pa:pb]
+                if dst is None:
+                    works.append(dist.all_reduce(piece, op=dist.ReduceOp.SUM, group=group, async_op=True))
+                else:
+                    works.append(dist.reduce(piece, dst=dst, op=dist.ReduceOp.SUM, group=group, async_op=True))
+        for w in works:
+            w.wait()                                        # main stream waits; the host does not
+
+    one_pass(None)
+    # ---- status, peaks, and the rare second pass of apply_hrtf.py:462-464 (see render_sources) ---------
+    flag = torch.zeros(1, dtype=torch.int32, device=torch_dev)
+    peaks_host = None
+    if job is not None:
+        small = job.small.cpu().numpy()
+        err, where = decode_status(small)
+        if err:
+            ah._raise_plan_error(err, ' (trajectory point %d of local source %d, rank %d)' % (where % job.n_pts, where // job.n_pts, rank))
+        peaks_host = small[2:].view(np.float32)
+        if normalise and (peaks_host > 1).any():
+            flag.fill_(1)
+    if normalise:
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+        if int(flag):
+            gains = None
+            if job is not None:
+                gains = torch.from_numpy((1.0 / np.maximum(peaks_host, 1.0)).astype(np.float32)).to(torch_dev)
+                job.zero_peaks()
+            else:
+                mix.zero_()
+            one_pass(gains)
+    result = mix[:, :n_out]
+    if dst is None or rank == dst:
+        return result
+    return None
+
+
+def _render_mix_injected(torch, dist, signals, chunksize, subchunksize, elev_azim_functions, bank, group, dst, render, normalise):
+    """The same exchange around an injected local renderer (CPU tests): render, then one collective."""
     if len(signals):
         local = render(signals, chunksize, subchunksize, elev_azim_functions, bank, mix=True,
                        normalise=normalise, return_device=True)
@@ -65,7 +185,7 @@ def render_mix_by_source(signals, chunksize, subchunksize, elev_azim_functions, 
         local = None
     local = _as_tensor(torch, local)
     if local is not None:
-        local = local.contiguous()                  # the renderer returns a view of a padded buffer; NCCL wants dense
+        local = local.contiguous()
     # ranks without sources contribute zeros of the right shape
     shape = torch.tensor([0, 0] if local is None else list(local.shape), dtype=torch.int64,
                          device=local.device if local is not None else _collective_device(torch, dist, group))
@@ -92,7 +212,8 @@ def render_by_time(in_signal, chunksize, subchunksize, elev_azim_function, bank,
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     n = in_signal.shape[0]
     k, n_in, n_out = render_geometry(n, chunksize, subchunksize, bank)
-    p0, p1 = time_segments(n_in, chunksize, k, world)[rank]
+    ranges = time_segments(n_in, chunksize, k, world)
+    p0, p1 = ranges[rank]
     n0, n1 = segment_inputs(p0, p1, n_in, chunksize, k)
     seg = None
     if p1 > p0:
@@ -117,10 +238,18 @@ def render_by_time(in_signal, chunksize, subchunksize, elev_azim_function, bank,
         _divide_by_peak(torch, seg, peak)                               # :463-464, only when the peak exceeds 1
     if not gather:
         return seg, (p0, p1)
-    full = torch.zeros((2, n_out), dtype=torch.float32, device=dev)
+    # all-gather of the time segments: every rank contributes its own (2, longest) block - each output byte
+    # crosses NVLink once per receiver - and the blocks are cut back to their true lengths
+    longest = max(b - a for a, b in ranges)
+    block = torch.zeros((2, longest), dtype=torch.float32, device=dev)
     if seg is not None:
-        full[:, p0:p1] = seg
-    dist.all_reduce(full, op=dist.ReduceOp.SUM, group=group)            # disjoint ranges: a gather
+        block[:, :p1 - p0] = seg
+    blocks = [torch.empty_like(block) for _ in range(world)]
+    dist.all_gather(blocks, block, group=group)
+    full = torch.empty((2, n_out), dtype=torch.float32, device=dev)
+    for (a, b), blk in zip(ranges, blocks):
+        if b > a:
+            full[:, a:b] = blk[:, :b - a]
     out = full.cpu().numpy() if full.is_cuda else full.numpy()
     return out.T
 
@@ -145,14 +274,18 @@ def _divide_by_peak(torch, seg, peak):
 
 def _shift_trajectory(fn, offset: int):
     """Trajectory seen from a window that starts at global sample `offset`."""
-    if getattr(fn, 'vectorized', False):
+    declared = getattr(fn, 'vectorized', None)
+    if declared:
         def shifted(t):
             return fn(np.asarray(t) + offset)
         shifted.vectorized = True
         if hasattr(fn, 'az_kind'):
             shifted.az_kind = fn.az_kind
         return shifted
-    return lambda t: fn(t + offset)
+    shifted = lambda t: fn(t + offset)                  # noqa: E731
+    if declared is False:
+        shifted.vectorized = False
+    return shifted
 
 
 def _as_tensor(torch, value):

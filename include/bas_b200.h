@@ -86,10 +86,10 @@ int bas_bank_delay_diffs(const double* hrir_dev, int n_rows, int n, int U, const
  * diffs_*_dev: 187 x 187 doubles row-major.  elev/azim: n_points doubles (radians).
  * az_kind_dev: n_points bytes (BAS_AZ_*), or NULL to use az_kind_all for every point.
  * terms_dev:   n_points x 2 x BAS_MAX_TERMS.   trace_dev: n_points records or NULL.
- * status_dev:  2 ints: [0] OR of the error bits of all points; [1] the minimum over failing points of
- *              (point index << 3 | error bits of that point) - index and bits of the EARLIEST failing
- *              point, which is where the reference would have raised (0x7f7f7f7f when none failed;
- *              indices are capped at BAS_STATUS_MAX_INDEX). */
+ * status_dev:  2 ints, zeroed by the call: [0] OR of the error bits of all points; [1] the bitwise
+ *              complement of min over failing points of (point index << 3 | error bits of that point) -
+ *              index and bits of the EARLIEST failing point, which is where the reference would have
+ *              raised.  All-zero words = no error (indices are capped at BAS_STATUS_MAX_INDEX). */
 #define BAS_STATUS_MAX_INDEX 0x0fffffff
 int bas_plan_build(const double* diffs_left_dev, const double* diffs_right_dev, int U, int L,
                    const double* elev_dev, const double* azim_dev, const uint8_t* az_kind_dev,
@@ -179,6 +179,61 @@ int bas_render(const float* x_dev, long long x_stride, long long n_valid, int n_
                long long p_begin, long long p_count, float* out_dev, long long out_stride, int mix,
                float* peaks_dev, int variant, void* workspace_dev, long long workspace_bytes, void* stream);
 
+/* The same renderer with the filter rows synthesised inside the tiled kernel (interpolate_2d's array part,
+ * apply_hrtf.py:219-281, fused into the chunk loop of :431-453): instead of filt_dev it takes the plan terms
+ * of bas_plan_build for n_src x (n_in/C + 1) chunk boundaries and the bank in the layout of
+ * bas_bank2_floats(): the polyphase bank of bas_bank_to_polyphase with every phase row stored twice in a
+ * row, [ear][row][U][2K] floats followed by padding (total bas_bank2_floats(U, K) floats), so that the
+ * circular index (m - adv) mod K is the plain index m + K - adv.  Rows are bit-identical to bas_ir_synth's.
+ * Needs the tiled kernel (S == 32, 32 | C, see bas_render_fused_supported); BAS_E_UNSUPPORTED otherwise. */
+int bas_render_fused(const float* x_dev, long long x_stride, long long n_valid, int n_src, long long n_in,
+                     int C, int S, int K, const bas_term* terms_dev, const float* bank_pp2_dev, int U,
+                     const float* gains_dev, long long p_begin, long long p_count, float* out_dev, long long out_stride,
+                     int mix, float* peaks_dev, int variant, void* workspace_dev, long long workspace_bytes, void* stream);
+int bas_render_fused_supported(int C, int S);
+long long bas_bank2_floats(int U, int K);
+
+/* ---- one render step as one call: apply_hrtf.py:429-435 feeding :438-453 and :459-464 ----------
+ * bas_render_step enqueues, on `stream`: [BAS_STEP_PLAN] one memset of small_dev, bas_plan_build for the
+ * n_src x (n_in/C + 1) directions, and (unless BAS_STEP_FUSED) bas_ir_synth into filt_dev;
+ * [BAS_STEP_RENDER] bas_render / bas_render_fused of output samples [p_begin, p_begin + p_count);
+ * [BAS_STEP_NORMALISE] (mix == 0) bas_normalise of every source by its own peak.  The kernels of one call
+ * are chained with programmatic dependent launch.  A job whose output is rendered in several time segments
+ * calls once with BAS_STEP_PLAN and then once per segment with BAS_STEP_RENDER. */
+#define BAS_STEP_PLAN 1
+#define BAS_STEP_RENDER 2
+#define BAS_STEP_NORMALISE 4
+#define BAS_STEP_FUSED 8
+typedef struct bas_step_job {
+    int n_src;                    /* mono sources */
+    int C, S, K, U;               /* chunksize, subchunksize, taps, upsampling of the bank */
+    int mix;                      /* 0, 1 or BAS_MIX_ACCUMULATE, as in bas_render */
+    int variant;                  /* bas_render variant */
+    int az_kind_all;              /* BAS_AZ_* of every direction when az_kind_dev is NULL */
+    int flags;                    /* BAS_STEP_* */
+    int reserved;
+    long long n_valid, n_in;      /* samples per source / rounded up to a multiple of C */
+    long long x_stride;           /* floats between sources in x_dev */
+    long long p_begin, p_count;   /* rendered output range */
+    long long out_stride;         /* floats between the ear rows of out_dev */
+    const float* x_dev;
+    const double* elev_dev;       /* n_src x (n_in/C + 1) directions (radians) */
+    const double* azim_dev;
+    const uint8_t* az_kind_dev;   /* or NULL */
+    const double* diffs_left_dev; /* bank: delay tables, polyphase HRIRs, and the doubled layout for FUSED */
+    const double* diffs_right_dev;
+    const float* bank_pp_dev;
+    const float* bank_pp2_dev;
+    bas_term* terms_dev;          /* scratch: n_src x (n_in/C + 1) x 2 x BAS_MAX_TERMS */
+    float* filt_dev;              /* scratch: n_src x (n_in/C + 1) filter rows (unused with BAS_STEP_FUSED) */
+    const float* gains_dev;       /* or NULL */
+    float* out_dev;
+    int32_t* small_dev;           /* 2 + n_src words: status pair (bas_plan_build), then per-source peaks */
+    void* workspace_dev;          /* bas_render workspace (may be NULL) */
+    long long workspace_bytes;
+} bas_step_job;
+int bas_render_step(const bas_step_job* job, void* stream);
+
 /* Scratch the tiled renderer may use to balance work across SMs: a tile split between two CTAs is
  * handed from one to the other through it (partial sums + a release/acquire flag per stripe, added
  * in a fixed order, so results stay deterministic).  workspace_dev may be NULL: tiles are then never
@@ -248,6 +303,9 @@ typedef struct bas_pipeline_job {
     void* stream_main;            /* three distinct streams */
     void* stream_up;
     void* stream_down;
+    const float* bank_pp2_dev;    /* bank in the bas_bank2_floats layout, or NULL.  When given and
+                                     bas_render_fused_supported(C, S), no filter rows are written: the render
+                                     kernel synthesises them (bas_render_fused) */
 } bas_pipeline_job;
 
 /* Bytes of device scratch a job needs.  offsets (may be NULL) receives the byte offsets of

@@ -107,10 +107,11 @@ def test_config5_full_length_irs_n16_bank(bas, oracle):
     assert rel_l2(once, each[:3]) <= 1e-6
 
 
-def test_grouped_mix_equals_one_launch(bas, synth_bank, monkeypatch):
-    """Mixing more than MIX_GROUP_SOURCES device-resident sources runs as groups: plan + ir_synth of the
-    next group on a side stream while the previous group renders, every later group ADDED to the mix
-    (BAS_MIX_ACCUMULATE).  Same mix as the one-launch path up to the order of the group sums."""
+def test_fused_filter_synthesis_is_bit_identical(bas, synth_bank, monkeypatch):
+    """The render kernel that synthesises its own filter rows (bas_render_fused, the default) against the
+    two-kernel path (bas_ir_synth writes the rows to HBM, bas_render copies them): same terms, same order of
+    summation, so the audio is bit-identical for a given tile shape - mixing and not, with a source that is
+    normalised on its own (gains pass), and a failing direction is reported with its source."""
     import torch
     ah = bas.apply_hrtf
     fs, n_src, n = 44100, 37, 40_000
@@ -120,15 +121,20 @@ def test_grouped_mix_equals_one_launch(bas, synth_bank, monkeypatch):
     trajs = [_lissajous(fs, 200 + s) for s in range(n_src)]
     xd = torch.zeros((n_src, (n + 511) // 512 * 512), dtype=torch.float32, device='cuda')
     xd[:, :n] = torch.from_numpy(x).cuda()
-    monkeypatch.setattr(ah, 'MIX_GROUP_SOURCES', 1000)
-    one, peaks_one = ah.render_sources(xd, 512, 32, trajs, synth_bank, mix=True, return_device=True, return_peaks=True)
-    one = one.cpu().numpy()
-    for group in (8, 16):
-        monkeypatch.setattr(ah, 'MIX_GROUP_SOURCES', group)
-        got, peaks = ah.render_sources(xd, 512, 32, trajs, synth_bank, mix=True, return_device=True, return_peaks=True)
-        assert np.array_equal(peaks, peaks_one) and peaks[20] > 1
-        assert rel_l2(got.cpu().numpy(), one) <= 1e-6
-    # a failing direction in a later group is reported with its source
+    for mix in (True, False):
+        for shape in (bas._cabi.render_variant(4, 1, 3, 1), bas._cabi.render_variant(8, 2, 1, 2), bas._cabi.render_variant(6, 1, 2, 1, split=True)):
+            monkeypatch.setattr(ah, 'FUSED', False)
+            two, peaks_two = ah.render_sources(xd, 512, 32, trajs, synth_bank, mix=mix, return_device=True, return_peaks=True, variant=shape)
+            monkeypatch.setattr(ah, 'FUSED', True)
+            one, peaks_one = ah.render_sources(xd, 512, 32, trajs, synth_bank, mix=mix, return_device=True, return_peaks=True, variant=shape)
+            assert np.array_equal(peaks_one, peaks_two) and peaks_one[20] > 1
+            assert torch.equal(one, two), (mix, shape)
+    # host arrays (pipeline.cu) take the fused kernel too
+    monkeypatch.setattr(ah, 'FUSED', False)
+    two = ah.render_sources(x[:5], 512, 32, trajs[:5], synth_bank, mix=True)
+    monkeypatch.setattr(ah, 'FUSED', True)
+    one = ah.render_sources(x[:5], 512, 32, trajs[:5], synth_bank, mix=True)
+    assert rel_l2(one, two) <= 1e-6                             # the library picks the tile shape per call
     bad = list(trajs)
     bad[30] = lambda t: (0.0, float('nan'))
     with pytest.raises(AssertionError, match='source 30'):
