@@ -368,8 +368,8 @@ def render_geometry(n_samples: int, chunksize: int, subchunksize: int, irs_and_d
 # the reference's loop.  A callable can opt out (`fn.vectorized = False`) or declare itself array-safe
 # and skip the checks (`fn.vectorized = True`, optionally `fn.az_kind`).
 TRAJECTORY_TRIAL_MIN = 24        # fewer boundaries than this: just loop
-TRAJECTORY_CHECKS = 16           # scalar spot checks of the first array evaluation of a callable
-TRAJECTORY_RECHECKS = 3          # spot checks of later evaluations (later phases of the same call)
+TRAJECTORY_CHECKS = 8            # scalar spot checks of the first array evaluation of a callable (first, last, random)
+TRAJECTORY_RECHECKS = 2          # spot checks of later evaluations (later phases of the same call): 12 per 3-phase call
 
 
 def _scalar_point(elev_azim_function, t):
@@ -586,15 +586,20 @@ _host_cache = _HostCache()
 # i+1 is evaluated on the host while phase i renders and travels back; a small first phase gets the
 # device -> host copy started early.  Jobs below PIPELINE_PHASE_MIN_BYTES run as one phase.
 PIPELINE_PHASES = (0.15, 0.5, 1.0)
+# many sources: the signal upload (4 B per source sample) is the long pole, not the download (8 B per MIXED pair);
+# more, shorter phases leave little to render after the last upload byte has arrived
+PIPELINE_PHASES_MANY = (0.08, 0.2, 0.35, 0.5, 0.65, 0.8, 0.92, 1.0)
 PIPELINE_PHASE_MIN_BYTES = 4 << 20
 
 
-def _phase_plan(p0: int, p1: int, n_in: int, chunksize: int, out_bytes_per_sample: int):
+def _phase_plan(p0: int, p1: int, n_in: int, chunksize: int, out_bytes_per_sample: int, n_src: int = 1):
     """[(p_from, p_to, pt_begin, pt_end)] per phase: output range and the chunk-boundary directions
     that must be planned before it renders (every input below p_to needs both filters of its chunk)."""
     n_pts = n_in // chunksize + 1
     count = p1 - p0
     fracs = PIPELINE_PHASES if count * out_bytes_per_sample >= PIPELINE_PHASE_MIN_BYTES else (1.0,)
+    if n_src >= 4 and count * 4 * n_src >= 4 * PIPELINE_PHASE_MIN_BYTES:
+        fracs = PIPELINE_PHASES_MANY
     cuts = [p0]
     for f in fracs[:-1]:
         c = min(p1, _round_up(p0 + int(f * count), _SEGMENT_ALIGN))
@@ -720,7 +725,7 @@ def _render_pipeline(torch, dev, src, chunksize, subchunksize, elev_azim_functio
         stream_main=main.cuda_stream, stream_up=up.cuda_stream, stream_down=down.cuda_stream,
         bank_pp2_dev=dev.bank_pp2.data_ptr() if FUSED else None)
     fused = bool(FUSED and (variant & 0x3f) != _cabi.RENDER_GENERIC and lib.bas_render_fused_supported(chunksize, subchunksize))
-    phases = _phase_plan(p0, p1, n_in, chunksize, 8 * n_rows)
+    phases = _phase_plan(p0, p1, n_in, chunksize, 8 * n_rows, n_src)
     cuts = (C.c_longlong * (len(phases) + 1))(*([ph[0] for ph in phases] + [p1]))
     _cabi.check(lib.bas_pipeline_upload(C.byref(job), len(phases), cuts), 'bas_pipeline_upload')
     staged_np = staged.numpy()

@@ -40,6 +40,11 @@ int bas_plan_build_range(const double* diffs_left_dev, const double* diffs_right
                          int az_kind_all, long long n_points, bas_term* terms_dev, bas_trace* trace_dev,
                          int* status_dev, long long point_offset, int reset_status, void* stream);
 
+int bas_plan_build_runs(const double* diffs_left_dev, const double* diffs_right_dev, int U, int L,
+                        const double* elev_dev, const double* azim_dev, const uint8_t* az_kind_dev,
+                        int az_kind_all, long long rows, long long run, long long run_stride, bas_term* terms_dev, bas_trace* trace_dev,
+                        int* status_dev, long long point_offset, int reset_status, void* stream);
+
 int bas_plan_build_inline(const double* diffs_left_dev, const double* diffs_right_dev, int U, int L,
                           const double* elev_host, const double* azim_host, int az_kind_all, long long n_points,
                           bas_term* terms_dev, int* status_dev, long long point_offset, void* stream);

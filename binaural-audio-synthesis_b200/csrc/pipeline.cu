@@ -181,21 +181,42 @@ extern "C" int bas_pipeline_phase(const bas_pipeline_job* j, int phase, int n_ph
     if (m > 0) {
         double* dirs = reinterpret_cast<double*>(arena + l.dirs);
         uint8_t* kinds = reinterpret_cast<uint8_t*>(arena + l.kinds);
-        if (j->az_kind_host) {
-            if (int rc = bas_copy_2d(dirs + pt_begin, l.n_pts * 8, j->dirs_host + pt_begin, l.n_pts * 8, m * 8, 2LL * j->n_src, 1, mainst)) return rc;
-            if (int rc = bas_copy_2d(kinds + pt_begin, l.n_pts, j->az_kind_host + pt_begin, l.n_pts, m, j->n_src, 1, mainst)) return rc;
+        // One source, one az kind (make_signal_move_2d): the directions ride in the plan launches themselves.
+        // Several sources: ONE plan launch per phase that reads the directions in place from the caller's pinned
+        // buffer (mapped host memory - a few bytes per point over PCIe, next to megabytes of signal upload);
+        // if the buffer is not device-accessible they are copied first.
+        const bool inline_dirs = j->n_src == 1 && !j->az_kind_host;
+        const double* elev_src = nullptr;
+        const uint8_t* kinds_src = nullptr;
+        if (!inline_dirs) {
+            void* mapped = nullptr;
+            void* mapped_kinds = nullptr;
+            const bool direct = cudaHostGetDevicePointer(&mapped, const_cast<double*>(j->dirs_host), 0) == cudaSuccess &&
+                                (!j->az_kind_host || cudaHostGetDevicePointer(&mapped_kinds, const_cast<uint8_t*>(j->az_kind_host), 0) == cudaSuccess);
+            if (direct) {
+                elev_src = static_cast<const double*>(mapped);
+                kinds_src = static_cast<const uint8_t*>(mapped_kinds);
+            } else {
+                cudaGetLastError();
+                if (int rc = bas_copy_2d(dirs + pt_begin, l.n_pts * 8, j->dirs_host + pt_begin, l.n_pts * 8, m * 8, 2LL * j->n_src, 1, mainst)) return rc;
+                if (j->az_kind_host)
+                    if (int rc = bas_copy_2d(kinds + pt_begin, l.n_pts, j->az_kind_host + pt_begin, l.n_pts, m, j->n_src, 1, mainst)) return rc;
+                elev_src = dirs;
+                kinds_src = j->az_kind_host ? kinds : nullptr;
+            }
+            if (int rc = bas_plan_build_runs(j->diffs_left_dev, j->diffs_right_dev, j->U, j->K * j->U, elev_src + pt_begin, elev_src + l.n_dirs + pt_begin,
+                                             kinds_src ? kinds_src + pt_begin : nullptr, j->az_kind_all, j->n_src, m, l.n_pts,
+                                             terms + pt_begin * 2 * BAS_MAX_TERMS, nullptr, small, pt_begin, 0, mainst)) return rc;
+            mark("phase %lld plan (one launch)", phase, 0, mainst);
         }
         for (int s = 0; s < j->n_src; ++s) {
             const long long first = (long long)s * l.n_pts + pt_begin;
             bas_term* t = terms + first * 2 * BAS_MAX_TERMS;
-            if (j->az_kind_host) {
-                if (int rc = bas_plan_build_range(j->diffs_left_dev, j->diffs_right_dev, j->U, j->K * j->U, dirs + first,
-                                                  dirs + l.n_dirs + first, kinds + first, 0, m, t, nullptr, small, first, 0, mainst)) return rc;
-            } else {
+            if (inline_dirs) {
                 if (int rc = bas_plan_build_inline(j->diffs_left_dev, j->diffs_right_dev, j->U, j->K * j->U, j->dirs_host + first,
                                                    j->dirs_host + l.n_dirs + first, j->az_kind_all, m, t, small, first, mainst)) return rc;
+                mark("phase %lld plan of source 0", phase, 0, mainst);
             }
-            if (s == 0) mark("phase %lld plan of source 0", phase, 0, mainst);
             if (!fused)
                 if (int rc = bas_ir_synth(j->bank_pp_dev, j->U, j->K, t, m, BAS_IR_ROWS, filt + first * l.pitch * 2, j->K, mainst)) return rc;
         }

@@ -68,12 +68,15 @@ bas_plan_kernel(const double* __restrict__ diffs_l, const double* __restrict__ d
                 const double* __restrict__ elev, const double* __restrict__ azim,
                 const uint8_t* __restrict__ az_kind, int az_kind_all, long long n_points,
                 BasTerm* __restrict__ terms, BasTrace* __restrict__ trace, int* __restrict__ status,
-                long long point_offset) {
+                long long point_offset, long long run, long long run_stride) {
     bas_grid_launch_dependents();
     bas_grid_dependency_wait();
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long p = t >> 1;
-    if (p >= n_points) return;
+    const long long q = t >> 1;
+    if (q >= n_points) return;
+    // the n_points points are `run` consecutive entries out of every `run_stride` (the same stretch of every
+    // source's trajectory); run == run_stride: one contiguous list
+    const long long p = run == run_stride ? q : (q / run) * run_stride + q % run;
     plan_thread(diffs_l, diffs_r, U, L, elev[p], azim[p], az_kind ? (int)az_kind[p] : az_kind_all, p, (int)(t & 1),
                 terms, trace, status, point_offset);
 }
@@ -103,6 +106,19 @@ int bas_plan_build_range(const double* diffs_left_dev, const double* diffs_right
                          const double* elev_dev, const double* azim_dev, const uint8_t* az_kind_dev,
                          int az_kind_all, long long n_points, bas_term* terms_dev, bas_trace* trace_dev,
                          int* status_dev, long long point_offset, int reset_status, void* stream) {
+    return bas_plan_build_runs(diffs_left_dev, diffs_right_dev, U, L, elev_dev, azim_dev, az_kind_dev, az_kind_all, 1, n_points, n_points,
+                               terms_dev, trace_dev, status_dev, point_offset, reset_status, stream);
+}
+
+// `rows` runs of `run` consecutive points, run_stride entries apart in every array (the same stretch of the
+// trajectory of every source), in ONE launch.
+int bas_plan_build_runs(const double* diffs_left_dev, const double* diffs_right_dev, int U, int L,
+                        const double* elev_dev, const double* azim_dev, const uint8_t* az_kind_dev,
+                        int az_kind_all, long long rows, long long run, long long run_stride, bas_term* terms_dev, bas_trace* trace_dev,
+                        int* status_dev, long long point_offset, int reset_status, void* stream) {
+    const long long n_points = rows * run;
+    BAS_CHECK_ARG(rows >= 0 && run >= 0 && (rows <= 1 || run_stride >= run), "runs");
+    if (rows <= 1) run_stride = run;
     BAS_CHECK_ARG(diffs_left_dev && diffs_right_dev && elev_dev && azim_dev && terms_dev, "null pointer");
     BAS_CHECK_ARG(U >= 1 && L >= U && L % U == 0 && L < (1 << 20), "need 1 <= U, U | L, L < 2^20");
     BAS_CHECK_ARG(az_kind_all >= 0 && az_kind_all <= 2, "az_kind_all");
@@ -117,7 +133,8 @@ int bas_plan_build_range(const double* diffs_left_dev, const double* diffs_right
     BAS_CHECK_ARG(blocks < 0x7fffffffLL, "too many points for one launch");
     BAS_CUDA(bas_launch(bas_plan_kernel, dim3((unsigned)blocks), dim3(threads), 0, st,
                         diffs_left_dev, diffs_right_dev, U, (long long)L, elev_dev, azim_dev, az_kind_dev, az_kind_all, n_points,
-                        reinterpret_cast<BasTerm*>(terms_dev), reinterpret_cast<BasTrace*>(trace_dev), status_dev, point_offset));
+                        reinterpret_cast<BasTerm*>(terms_dev), reinterpret_cast<BasTrace*>(trace_dev), status_dev, point_offset,
+                        run, run_stride));
     return 0;
 }
 

@@ -31,6 +31,7 @@ struct RenderParams {
     const TermDev* terms;          // [n_src][n_in/C + 1][2 ears][16] (bas_plan_build)
     const float* bank2;            // polyphase bank with every phase row stored twice: [ear][row][U][2K] (+ padding)
     int U;
+    int nf;                        // FUSED: filter-row buffers in shared memory (2: producers run one item ahead)
 };
 
 __device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
@@ -165,11 +166,25 @@ __host__ __device__ inline size_t tmap_stage_bytes(const TileGeom& g) {
     return (x + g.f_bytes + 1023) / 1024 * 1024;                  // every stage starts on a swizzle atom
 }
 constexpr int kTermsPerRow = 2 * BAS_MAX_TERMS;             // both ears
-__host__ __device__ inline size_t tile_smem_bytes(const TileGeom& g, int TW, int NS, int parts, int C, bool mix, bool tmap, bool fused = false) {
+// FUSED kernels keep the input rows (staged by TMA) and the filter rows (synthesised by the producer warps)
+// apart: NS stages of input rows, then nf buffers of filter rows and one term table
+__host__ __device__ inline size_t fused_x_stage_bytes(const TileGeom& g, bool tmap) {
+    if (!tmap) return (size_t)g.x_bytes;
+    return ((size_t)tmap_n_box(g.x_rows) * tmap_box_rows(g.x_rows) * 128 + 1023) / 1024 * 1024;
+}
+__host__ __device__ inline size_t tile_smem_bytes(const TileGeom& g, int TW, int NS, int parts, int C, bool mix, bool tmap, bool fused = false, int nf = 0) {
     const int TS = TW / parts;
-    const size_t staging = tmap ? 1024 + (size_t)NS * tmap_stage_bytes(g) : (size_t)NS * g.stage_bytes + (size_t)TW * g.warp_x_bytes;
-    return kBarBytes + staging + (size_t)((C / kBlk * 4 + 15) / 16 * 16) + (fused ? (size_t)g.f_rows * kTermsPerRow * 8 : 0) +
+    size_t staging;
+    if (fused) staging = (tmap ? 1024 : (size_t)TW * g.warp_x_bytes) + (size_t)NS * fused_x_stage_bytes(g, tmap);
+    else staging = tmap ? 1024 + (size_t)NS * tmap_stage_bytes(g) : (size_t)NS * g.stage_bytes + (size_t)TW * g.warp_x_bytes;
+    return kBarBytes + staging + (size_t)((C / kBlk * 4 + 15) / 16 * 16) +
+           (fused ? (size_t)g.f_rows * kTermsPerRow * 8 + (size_t)nf * g.f_bytes : 0) +
            (parts > 1 ? (size_t)(TW - TS) * kStripeBytes : 0) + (mix ? (size_t)TS * kStripeBytes : 0);
+}
+// FUSED shapes: TW consumer warps + TW / 2 producer warps, two input stages, and a register budget that still
+// gives the consumers their 168 registers: (4, 2, 2), (6, 2, 1), (8, 2, 1)
+__host__ __device__ constexpr bool fused_shape_ok(int TW, int NS, int MINB) {
+    return NS == 2 && ((TW == 4 && MINB == 2) || (TW == 6 && MINB == 1) || (TW == 8 && MINB == 1));
 }
 
 // One 32x32 block, visited diagonal by diagonal:  acc[r] += x_sel[m] * tap(r - m)  for r, m = 0..31 with
@@ -281,24 +296,30 @@ __device__ __forceinline__ void cta_barrier(int threads) {
 // the item's tap blocks; their partial sums meet in shared memory in a fixed order.  A tile is then
 // TW / parts stripes: smaller tiles and more of them, which is what fills the last wave of a launch
 // whose tile count is a small multiple of the resident warps.
-// FUSED: the boundary-filter rows an item needs are synthesised by the CTA's own warps straight into the
-// stage (interpolate_2d's array part, apply_hrtf.py:219-281, = ir_synth.cu's weighted gather) instead of being
-// copied from a filter-row array that a separate bas_ir_synth launch wrote: the gathers lean on L2 while the FMA
-// pipe idles, the FIR blocks are the exact complement, and with two or three CTAs per SM one CTA's gather
-// phase hides under its neighbours' FMA phase.  Same terms, same order of summation: bit-identical rows.
+// FUSED: the boundary-filter rows an item needs are not copied from a filter-row array that a separate
+// bas_ir_synth launch wrote; TW / 2 PRODUCER warps of the CTA synthesise them straight into shared memory
+// (interpolate_2d's array part, apply_hrtf.py:219-281, = ir_synth.cu's weighted gather from the L2-resident
+// polyphase bank) one item ahead of the TW CONSUMER warps, which run the FIR blocks.  The gathers lean on L2
+// while the FMA pipe idles, the FIR blocks are the exact complement: the two share every SM instead of taking
+// turns on the device.  Hand-over by mbarriers (full / empty per filter buffer and per input stage); the
+// producers also issue the TMA copies of the input rows.  Same terms, same order of summation: the rows
+// are bit-identical to bas_ir_synth's.
 template <int TW, bool MIX, int NS, int MINB, bool FUSED = false>
-__global__ void __launch_bounds__(TW * 32, MINB)
+__global__ void __launch_bounds__((FUSED ? TW + TW / 2 : TW) * 32, MINB)
 bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ workspace, const __grid_constant__ CUtensorMap xmap) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int P = prm.parts, TS = TW / P;
     const TileGeom g = tile_geom(prm.K, prm.C, prm.pitch, TS);
+    constexpr int PW = FUSED ? TW / 2 : 0;                // producer warps
     u64* full_bar = reinterpret_cast<u64*>(smem);              // [NS]
     u64* empty_bar = full_bar + NS;                       // [NS]
+    u64* full_f = empty_bar + NS;                         // [2]  FUSED: filter buffer written / ...
+    u64* empty_f = full_f + 2;                            // [2]  ... read by every consumer warp
     // tensor-map path: stages start on a 1024-byte boundary (the 128-byte swizzle works on address bits)
     const bool tmap = prm.tmap != 0;
     unsigned char* stage_base = smem + kBarBytes;
     if (tmap) stage_base += (1024u - (smem_u32(stage_base) & 1023u)) & 1023u;
-    const size_t stage_stride = tmap ? tmap_stage_bytes(g) : (size_t)g.stage_bytes;
+    const size_t stage_stride = FUSED ? fused_x_stage_bytes(g, tmap) : tmap ? tmap_stage_bytes(g) : (size_t)g.stage_bytes;
     const size_t x_stage_bytes = tmap ? (size_t)prm.n_box * prm.box_rows * 128 : (size_t)g.x_bytes;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -309,7 +330,8 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
     float* alpha_tab = reinterpret_cast<float*>(after_stages + (tmap ? 0 : (size_t)TW * g.warp_x_bytes));
     unsigned char* after_tab = reinterpret_cast<unsigned char*>(alpha_tab) + (spc * 4 + 15) / 16 * 16;
     int2* term_tab = reinterpret_cast<int2*>(after_tab);     // FUSED: {float offset into bank2, weight bits} per (row, ear, slot)
-    unsigned char* after_alpha = after_tab + (FUSED ? (size_t)g.f_rows * kTermsPerRow * 8 : 0);
+    unsigned char* fbuf_base = after_tab + (FUSED ? (size_t)g.f_rows * kTermsPerRow * 8 : 0);       // FUSED: nf filter-row buffers
+    unsigned char* after_alpha = fbuf_base + (FUSED ? (size_t)prm.nf * g.f_bytes : 0);
     // partial sums of parts 1..P-1 of every stripe: [stripe][part - 1][r][lane] {L,R}
     u64* red = reinterpret_cast<u64*>(after_alpha);
     u64* mixbuf = reinterpret_cast<u64*>(after_alpha + (P > 1 ? (size_t)(TW - TS) * kStripeBytes : 0)) + (size_t)stripe * kWarpTile;
@@ -327,9 +349,10 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
 
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, TW); }
+        if (FUSED) for (int s = 0; s < 2; ++s) { mbar_init(full_f + s, PW * 32); mbar_init(empty_f + s, TW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int s = tid; s < spc; s += TW * 32) alpha_tab[s] = (float)(s * kBlk) / (float)prm.C;      // apply_hrtf.py:442
+    for (int s = tid; s < spc; s += (TW + PW) * 32) alpha_tab[s] = (float)(s * kBlk) / (float)prm.C;      // apply_hrtf.py:442
     __syncthreads();
     // programmatic dependent launch: everything above overlapped the tail of the previous kernel in the
     // stream; the filter rows / plan terms it wrote are read only from here on
@@ -421,7 +444,75 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
         __syncwarp();
     };
 
-    if (warp == 0 && n_items > 0) produce(0);
+    if (FUSED && warp >= TW) {
+        // =========================== producer warps (FUSED) ===========================================
+        // For every item, in order: the TMA copies of its input rows into stage j % NS (first producer warp), then its
+        // filter rows into buffer j % nf:   row[m] = sum_t w_t * bank[row_t][phase_t][(m - adv_t) mod K]   per ear,
+        // the terms in their fixed plan slots (a slot with weight zero reads the bank's first phase row with weight
+        // zero: adds exactly nothing), summed in slot order like ir_synth.cu.  Every phase row is stored twice in
+        // a row, so (m - adv) mod K is the plain index m + K - adv.
+        constexpr int PT = PW * 32;
+        constexpr int G = 3;                                    // (row, tap) units per thread and pass: 96 loads in flight
+        const int ptid = tid - TW * 32;
+        const int K = prm.K, K2 = 2 * prm.K;
+        for (int j = 0; j < n_items; ++j) {
+            if (warp == TW) produce(j);
+            const Item it = item_info(j);
+            long long n_lo, c_first; int n_rows;
+            tile_chunks(it.tile, n_lo, c_first, n_rows);
+            const int fb = j % prm.nf;
+            if (j >= prm.nf) mbar_wait(empty_f + fb, (unsigned)((j / prm.nf - 1) & 1));      // consumers left the buffer
+            asm volatile("bar.sync 2, %0;" ::"r"(PT) : "memory");                            // ... and every producer the table
+            const TermDev* tsrc = prm.terms + ((long long)it.src * (n_chunks + 1) + c_first) * kTermsPerRow;
+            for (int e = ptid; e < n_rows * kTermsPerRow; e += PT) {
+                const TermDev t = tsrc[e];
+                const int ear = (e & (kTermsPerRow - 1)) / BAS_MAX_TERMS;
+                const int row = t.row_shift >> 20, shift = t.row_shift & 0xFFFFF;
+                const int ph = (prm.U - shift % prm.U) % prm.U;
+                const int adv = (shift + ph) / prm.U;
+                const int off = t.weight != 0.f ? ((ear * BAS_N_DIRECTIONS + row) * prm.U + ph) * K2 + K - adv : 0;
+                term_tab[e] = make_int2(off, __float_as_int(t.weight));
+            }
+            asm volatile("bar.sync 2, %0;" ::"r"(PT) : "memory");
+            float2* fsw = reinterpret_cast<float2*>(fbuf_base + (size_t)fb * g.f_bytes);
+            // units u = row * K + tap, dealt round-robin over the producer threads; a warp's lanes share the row
+            // whenever 32 | K, so the table reads below are broadcasts
+            int row = 0, tap = ptid;
+            while (tap >= K) { tap -= K; ++row; }
+            while (row < n_rows) {
+                float v[G][kTermsPerRow];
+                int urow[G], utap[G];
+#pragma unroll
+                for (int u = 0; u < G; ++u) {
+                    urow[u] = row; utap[u] = tap;
+                    const int2* tab = term_tab + (row < n_rows ? row : n_rows - 1) * kTermsPerRow;
+                    const float* b0 = prm.bank2 + tap;
+#pragma unroll
+                    for (int t = 0; t < kTermsPerRow; ++t) v[u][t] = __ldg(b0 + tab[t].x);
+                    tap += PT;
+                    while (tap >= K) { tap -= K; ++row; }
+                }
+#pragma unroll
+                for (int u = 0; u < G; ++u) {
+                    if (urow[u] < n_rows) {
+                        const int2* tab = term_tab + urow[u] * kTermsPerRow;
+                        float l = 0.f, r = 0.f;
+#pragma unroll
+                        for (int t = 0; t < BAS_MAX_TERMS; ++t) {
+                            l = fmaf(__int_as_float(tab[t].y), v[u][t], l);
+                            r = fmaf(__int_as_float(tab[BAS_MAX_TERMS + t].y), v[u][BAS_MAX_TERMS + t], r);
+                        }
+                        fsw[urow[u] * prm.pitch + utap[u]] = make_float2(l, r);
+                    }
+                }
+            }
+            const int pad = prm.pitch - K;                           // zero padding taps K .. pitch - 1 of every row
+            for (int e = ptid; e < n_rows * pad; e += PT) fsw[(e / pad) * prm.pitch + K + e % pad] = make_float2(0.f, 0.f);
+            mbar_arrive(full_f + fb);                                // every producer thread: its own stores are released
+        }
+        return;
+    }
+    if (!FUSED && warp == 0 && n_items > 0) produce(0);
 
     if (MIX && part == 0) {
 #pragma unroll
@@ -434,7 +525,7 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
     for (int j = 0; j < n_items; ++j) {
         // two stages: the copy of item j+1 overlaps the arithmetic of item j.  One stage: the slot can
         // only be refilled after every warp (this one included) has left it - see below.
-        if (NS > 1 && warp == 0 && j + 1 < n_items) produce(j + 1);
+        if (!FUSED && NS > 1 && warp == 0 && j + 1 < n_items) produce(j + 1);
         const int st = j % NS;
         const Item it = item_info(j);
         long long n_lo, c_first; int n_rows;
@@ -442,65 +533,20 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
         const long long P0 = p_base + it.tile * T;
         const bool warp_live = P0 + (long long)stripe * kWarpTile < prm.p_end;
         const float* xs = reinterpret_cast<const float*>(stage_base + (size_t)st * stage_stride);
-        const float2* fs = reinterpret_cast<const float2*>(stage_base + (size_t)st * stage_stride + x_stage_bytes);
+        const int fb = FUSED ? j % prm.nf : 0;
+        const float2* fs = FUSED ? reinterpret_cast<const float2*>(fbuf_base + (size_t)fb * g.f_bytes)
+                                 : reinterpret_cast<const float2*>(stage_base + (size_t)st * stage_stride + x_stage_bytes);
         const long long q0 = n_lo / kBlk;                       // exact (n_lo % 32 == 0), may be negative
         // this warp's share of the item's tap blocks
         const int len = it.d1 - it.d0;
         const int d_first = it.d0 + (len * part) / P, d_last = it.d0 + (len * (part + 1)) / P;
 
-        if (FUSED) {
-            // ---- filter rows of this item: out[m] = sum_t w_t * bank[row_t][phase_t][(m - adv_t) mod K] per ear, the
-            //      terms in their fixed plan slots (a slot with weight zero reads column m of the bank's first
-            //      phase row with weight zero: adds exactly nothing), summed in slot order like ir_synth.cu.
-            //      Every phase row is stored twice in a row, so (m - adv) mod K is the plain index m + K - adv.
-            cta_barrier(TW * 32);                           // every warp has left the previous item's rows and table
-            const TermDev* tsrc = prm.terms + ((long long)it.src * (n_chunks + 1) + c_first) * kTermsPerRow;
-            const int K2 = 2 * prm.K;
-            for (int e = tid; e < n_rows * kTermsPerRow; e += TW * 32) {
-                const TermDev t = tsrc[e];
-                const int ear = (e & (kTermsPerRow - 1)) / BAS_MAX_TERMS;
-                const int row = t.row_shift >> 20, shift = t.row_shift & 0xFFFFF;
-                const int ph = (prm.U - shift % prm.U) % prm.U;
-                const int adv = (shift + ph) / prm.U;
-                const int off = t.weight != 0.f ? ((ear * BAS_N_DIRECTIONS + row) * prm.U + ph) * K2 + prm.K - adv : 0;
-                term_tab[e] = make_int2(off, __float_as_int(t.weight));
-            }
-            cta_barrier(TW * 32);
-            float2* fsw = reinterpret_cast<float2*>(stage_base + (size_t)st * stage_stride + x_stage_bytes);
-            constexpr int T = TW * 32;
-            for (int r = 0; r < n_rows; ++r) {
-                const int2* tab = term_tab + r * kTermsPerRow;
-                float2* dst = fsw + r * prm.pitch;
-                // two taps per thread and pass (m, m + T): one table read serves both, the second load is the
-                // first address plus a constant (the bank carries padding, so it is always in bounds)
-                for (int m = tid; m < prm.K; m += 2 * T) {
-                    const float* b0 = prm.bank2 + m;
-                    float v0[kTermsPerRow], v1[kTermsPerRow];
-#pragma unroll
-                    for (int t = 0; t < kTermsPerRow; ++t) {
-                        const int off = tab[t].x;
-                        v0[t] = __ldg(b0 + off);
-                        v1[t] = __ldg(b0 + off + T);
-                    }
-                    float l0 = 0.f, r0 = 0.f, l1 = 0.f, r1 = 0.f;
-#pragma unroll
-                    for (int t = 0; t < BAS_MAX_TERMS; ++t) {
-                        const float wl = __int_as_float(tab[t].y), wr = __int_as_float(tab[BAS_MAX_TERMS + t].y);
-                        l0 = fmaf(wl, v0[t], l0); r0 = fmaf(wr, v0[BAS_MAX_TERMS + t], r0);
-                        l1 = fmaf(wl, v1[t], l1); r1 = fmaf(wr, v1[BAS_MAX_TERMS + t], r1);
-                    }
-                    dst[m] = make_float2(l0, r0);
-                    if (m + T < prm.K) dst[m + T] = make_float2(l1, r1);
-                }
-                for (int m = prm.K + tid; m < prm.pitch; m += T) dst[m] = make_float2(0.f, 0.f);     // zero padding taps
-            }
-            cta_barrier(TW * 32);
-        }
         u64 acc[kBlk];
 #pragma unroll
         for (int r = 0; r < kBlk; ++r) acc[r] = 0ull;
 
         mbar_wait(full_bar + st, (unsigned)((j / NS) & 1));
+        if (FUSED) mbar_wait(full_f + fb, (unsigned)((j / prm.nf) & 1));
 
         if (warp_live && d_last > d_first) {
             if (!tmap) {
@@ -562,7 +608,8 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty_bar + st);             // this warp is done with the slot
-        if (NS == 1 && warp == 0 && j + 1 < n_items) produce(j + 1);
+        if (FUSED && lane == 0) mbar_arrive(empty_f + fb);      // ... and with the filter rows
+        if (!FUSED && NS == 1 && warp == 0 && j + 1 < n_items) produce(j + 1);
 
         // ---- the warps of a stripe add up: parts 1.. hand their sums to part 0, fixed order ---------
         if (P > 1) {
@@ -703,19 +750,28 @@ inline int device_sm_count() {
 template <int TW, bool MIX, int NS, int MINB, bool FUSED>
 int tiled_ctas_per_sm(int K, int C, int pitch, int parts, bool tmap) {
     if (parts < 1 || TW % parts) return 0;
-    const TileGeom g = tile_geom(K, C, pitch, TW / parts);
-    const size_t smem = tile_smem_bytes(g, TW, NS, parts, C, MIX, tmap, FUSED);
-    if (smem > 227 * 1024) return 0;
-    auto kern = bas_render_tiled_kernel<TW, MIX, NS, MINB, FUSED>;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TW * 32, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
-    return per_sm;
+    if constexpr (FUSED && !fused_shape_ok(TW, NS, MINB)) {
+        return 0;
+    } else {
+        const TileGeom g = tile_geom(K, C, pitch, TW / parts);
+        size_t smem = tile_smem_bytes(g, TW, NS, parts, C, MIX, tmap, FUSED, 2);
+        if (FUSED && smem > 227 * 1024) smem = tile_smem_bytes(g, TW, NS, parts, C, MIX, tmap, FUSED, 1);
+        if (smem > 227 * 1024) return 0;
+        auto kern = bas_render_tiled_kernel<TW, MIX, NS, MINB, FUSED>;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (FUSED ? TW + TW / 2 : TW) * 32, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+        return per_sm;
+    }
 }
 
 template <int TW, bool MIX, int NS, int MINB, bool FUSED>
 int launch_tiled(RenderParams prm, int parts, bool want_split, float* workspace, long long workspace_bytes, cudaStream_t st) {
     if (parts < 1 || TW % parts) return BAS_E_UNSUPPORTED;
+    if constexpr (FUSED && !fused_shape_ok(TW, NS, MINB)) {
+        return BAS_E_UNSUPPORTED;
+    } else {
+    constexpr int kThreads = (FUSED ? TW + TW / 2 : TW) * 32;
     const int TS = TW / parts;
     const TileGeom g = tile_geom(prm.K, prm.C, prm.pitch, TS);
     // input rows by tensor-map TMA when the signal allows it (whole 32-sample rows, 16-byte aligned)
@@ -724,7 +780,9 @@ int launch_tiled(RenderParams prm, int parts, bool want_split, float* workspace,
     prm.n_box = tmap_n_box(g.x_rows);
     prm.box_rows = tmap_box_rows(g.x_rows);
     prm.tmap = make_input_tensor_map(&xmap, prm, prm.box_rows) ? 1 : 0;
-    const size_t smem = tile_smem_bytes(g, TW, NS, parts, prm.C, MIX, prm.tmap != 0, FUSED);
+    prm.nf = FUSED ? 2 : 0;
+    size_t smem = tile_smem_bytes(g, TW, NS, parts, prm.C, MIX, prm.tmap != 0, FUSED, prm.nf);
+    if (FUSED && smem > 227 * 1024) { prm.nf = 1; smem = tile_smem_bytes(g, TW, NS, parts, prm.C, MIX, prm.tmap != 0, FUSED, 1); }
     if (smem > 227 * 1024) return BAS_E_UNSUPPORTED;
     auto kern = bas_render_tiled_kernel<TW, MIX, NS, MINB, FUSED>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -742,7 +800,7 @@ int launch_tiled(RenderParams prm, int parts, bool want_split, float* workspace,
     }
     // persistent grid: as many CTAs as the device keeps resident
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TW * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem);
     if (e != cudaSuccess || per_sm < 1) { bas_set_error("bas_render: tile shape does not fit an SM"); cudaGetLastError(); return BAS_E_UNSUPPORTED; }
     long long grid = (long long)device_sm_count() * per_sm;
     if (grid > sp.n_groups) grid = sp.n_groups;
@@ -751,9 +809,10 @@ int launch_tiled(RenderParams prm, int parts, bool want_split, float* workspace,
     const long long need = (long long)ws_bytes(grid, TS);
     sp.split = (want_split && workspace && workspace_bytes >= need && grid > 1 && sp.total / grid >= sp.gs + 1) ? 1 : 0;
     sp.epoch = sp.split ? next_epoch() : 0ull;
-    e = bas_launch(kern, dim3((unsigned)grid), dim3(TW * 32), smem, st, prm, sp, workspace, xmap);
+    e = bas_launch(kern, dim3((unsigned)grid), dim3(kThreads), smem, st, prm, sp, workspace, xmap);
     if (e != cudaSuccess) { bas_set_error("bas_render: tiled launch failed: %s", cudaGetErrorString(e)); return (int)e; }
     return 0;
+    }
 }
 
 // One compiled tile shape: warps per CTA x pipeline stages x CTAs per SM the registers allow.

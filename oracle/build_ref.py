@@ -4,7 +4,7 @@
 
 TEST INFRASTRUCTURE ONLY.  The reference is pure Python, so its "binary" is CPython bytecode:
 /root/reference/apply_hrtf.py and sphere.py are compiled with py_compile straight into
-oracle/_ref/apply_hrtf.pyc and oracle/_ref/sphere.pyc (sourceless modules).  No reference source is
+oracle/_ref/apply_hrtf.bytecode and oracle/_ref/sphere.bytecode (sourceless modules).  No reference source is
 copied into the repository; oracle/_ref/ is git-ignored but travels to the GPU box with the snapshot
 (same image, same interpreter), where /root/reference does not exist.  Users: bench.py's cpu_baseline
 and `--impl reference` legs (kind "reference") and tests that re-check the oracle against it.
@@ -25,11 +25,11 @@ def build(verbose=True) -> bool:
         return False
     os.makedirs(OUT, exist_ok=True)
     for m in MODULES:
-        py_compile.compile(os.path.join(REFERENCE, m + '.py'), cfile=os.path.join(OUT, m + '.pyc'), doraise=True)
+        py_compile.compile(os.path.join(REFERENCE, m + '.py'), cfile=os.path.join(OUT, m + '.bytecode'), doraise=True)
     with open(os.path.join(OUT, 'BUILT_FROM'), 'w') as f:
         f.write('%s (python %s)\n' % (REFERENCE, sys.version.split()[0]))
     if verbose:
-        print('oracle/_ref: compiled %s from %s' % (', '.join(m + '.pyc' for m in MODULES), REFERENCE))
+        print('oracle/_ref: compiled %s from %s' % (', '.join(m + '.bytecode' for m in MODULES), REFERENCE))
     return True
 
 

@@ -17,7 +17,7 @@ REF_DIR = os.path.join(HERE, '_ref')
 
 
 def available() -> bool:
-    return all(os.path.exists(os.path.join(REF_DIR, m + '.pyc')) for m in ('apply_hrtf', 'sphere'))
+    return all(os.path.exists(os.path.join(REF_DIR, m + '.bytecode')) for m in ('apply_hrtf', 'sphere'))
 
 
 def load():
@@ -32,7 +32,7 @@ def load():
     mods = {}
     try:
         for name in ('sphere', 'apply_hrtf'):          # apply_hrtf does `import sphere`
-            loader = importlib.machinery.SourcelessFileLoader(name, os.path.join(REF_DIR, name + '.pyc'))
+            loader = importlib.machinery.SourcelessFileLoader(name, os.path.join(REF_DIR, name + '.bytecode'))
             spec = importlib.util.spec_from_loader(name, loader)
             mod = importlib.util.module_from_spec(spec)
             sys.modules[name] = mod
