@@ -251,6 +251,13 @@ extern "C" int bas_render_fused(const float* x_dev, long long x_stride, long lon
 
 extern "C" int bas_render_fused_supported(int C, int S) { return S == kBlk && C % kBlk == 0 ? 1 : 0; }
 
+extern "C" int bas_render_fused_shape(int variant) {
+    // 1 when the (TW, NS, CTAs per SM) a variant word requests is one the fused kernel is compiled for (or none is requested)
+    const int tw = (variant >> 8) & 0xff, ns = (variant >> 16) & 0xff, ctas = (variant >> 24) & 0xf;
+    if (!tw && !ns && !ctas) return 1;
+    return fused_shape_ok(tw, ns ? ns : 2, ctas ? ctas : (tw == 4 ? 2 : 1)) ? 1 : 0;
+}
+
 extern "C" long long bas_bank2_floats(int U, int K) {
     // every phase row twice + padding for the second tap of a gather pass (render_tiled.cuh)
     return U < 1 || K < 1 ? BAS_E_ARG : 2LL * BAS_N_DIRECTIONS * U * 2 * K + 1024;

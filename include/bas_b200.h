@@ -191,6 +191,7 @@ int bas_render_fused(const float* x_dev, long long x_stride, long long n_valid, 
                      const float* gains_dev, long long p_begin, long long p_count, float* out_dev, long long out_stride,
                      int mix, float* peaks_dev, int variant, void* workspace_dev, long long workspace_bytes, void* stream);
 int bas_render_fused_supported(int C, int S);
+int bas_render_fused_shape(int variant);      /* 1: the tile shape `variant` requests is compiled for the fused kernel */
 long long bas_bank2_floats(int U, int K);
 
 /* ---- one render step as one call: apply_hrtf.py:429-435 feeding :438-453 and :459-464 ----------

@@ -122,12 +122,13 @@ def test_fused_filter_synthesis_is_bit_identical(bas, synth_bank, monkeypatch):
     xd = torch.zeros((n_src, (n + 511) // 512 * 512), dtype=torch.float32, device='cuda')
     xd[:, :n] = torch.from_numpy(x).cuda()
     for mix in (True, False):
-        for shape in (bas._cabi.render_variant(4, 1, 3, 1), bas._cabi.render_variant(8, 2, 1, 2), bas._cabi.render_variant(6, 1, 2, 1, split=True)):
+        for shape in (bas._cabi.render_variant(4, 2, 2, 1), bas._cabi.render_variant(8, 2, 1, 2), bas._cabi.render_variant(6, 2, 1, 1, split=True), bas._cabi.render_variant(8, 2, 1, 1)):
             monkeypatch.setattr(ah, 'FUSED', False)
             two, peaks_two = ah.render_sources(xd, 512, 32, trajs, synth_bank, mix=mix, return_device=True, return_peaks=True, variant=shape)
             monkeypatch.setattr(ah, 'FUSED', True)
             one, peaks_one = ah.render_sources(xd, 512, 32, trajs, synth_bank, mix=mix, return_device=True, return_peaks=True, variant=shape)
             assert np.array_equal(peaks_one, peaks_two) and peaks_one[20] > 1
+            assert bas._cabi.lib.bas_render_fused_shape(shape) == 1     # the comparison is not the two-kernel path against itself
             assert torch.equal(one, two), (mix, shape)
     # host arrays (pipeline.cu) take the fused kernel too
     monkeypatch.setattr(ah, 'FUSED', False)
