@@ -526,7 +526,17 @@ def run_mix(ctx, name):
     mine = distributed.shard_sources(n_src, rank, world)
     n_local = len(mine)
     mix_mode = not weak
-    segs = distributed.mix_segments(n_out, args.segments) if mix_mode else [(0, n_out)]
+    collective = args.collective if (world > 1 and mix_mode) else 'none'
+    peer = None
+    if collective == 'peer':
+        peer = distributed._peer_mix(n_out, None)
+        ok = torch.tensor([1 if peer is not None else 0], dtype=torch.int32, device=ctx.dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if not int(ok):
+            peer, collective = None, 'all_reduce'
+    # device-resident inputs: one render launch per step (the exchange needs no time segments when it is fused
+    # with the render); --segments N cuts the output into N launches, each followed by its NCCL collective
+    segs = distributed.mix_segments(n_out, args.segments or 1) if mix_mode else [(0, n_out)]
 
     # ---- inputs resident in HBM: signals, directions.  Rotating sets so that a step's working set is not
     #      L2-resident from the step before (the 126 MB L2 would otherwise serve the signals) --------------
@@ -545,7 +555,6 @@ def run_mix(ctx, name):
         out = torch.zeros((2, stride) if mix_mode else (max(n_local, 1), 2, stride), dtype=torch.float32, device=ctx.dev)
         sets.append((job, out))
     st = ctx.stream.cuda_stream
-    collective = args.collective if (world > 1 and mix_mode) else 'none'
 
     def reduce_segment(out, pa, pb, works):
         for ear in range(2):
@@ -562,11 +571,19 @@ def run_mix(ctx, name):
             job.plan(st)
         for pa, pb in segs:
             if job is not None:
-                job.render(st, pa, pb, out.data_ptr() + 4 * pa, stride, normalise=not mix_mode)
-            if collective != 'none':
+                job.render(st, pa, pb, out.data_ptr() + 4 * pa, stride, normalise=not mix_mode, route=peer.route if peer is not None else None)
+            if collective in ('all_reduce', 'reduce'):
                 reduce_segment(out, pa, pb, works)        # NCCL stream: ordered after this render, beside the next one
+        if peer is not None:
+            if job is None:
+                peer.zero_my_blocks()
+            peer.finish(st)                               # signal, rank-order sum of this rank's slice, wait for all slices
         for w in works:
             w.wait()
+
+    def mix_of(i):
+        """Where step i leaves the global mix."""
+        return peer.result if peer is not None else sets[i % n_sets][1]
 
     def step_late_collective(i):
         """The round-1 arrangement, for comparison: one collective after the last render."""
@@ -575,10 +592,10 @@ def run_mix(ctx, name):
             job.plan(st)
             for pa, pb in segs:
                 job.render(st, pa, pb, out.data_ptr() + 4 * pa, stride)
-        if collective == 'all_reduce':
-            dist.all_reduce(out)
-        elif collective == 'reduce':
+        if collective == 'reduce':
             dist.reduce(out, dst=0)
+        elif collective != 'none':
+            dist.all_reduce(out)
 
     def render_only(i):
         job, out = sets[i % n_sets]
@@ -605,7 +622,7 @@ def run_mix(ctx, name):
             assert not mix_mode or float(small[2:].view(np.float32).max()) <= 1.0
     per_rank = ctx.gather_objects({'rank': rank, 'mean_ms': float(np.mean(per_step)), 'min_ms': float(np.min(per_step)),
                                    'median_ms': float(np.median(per_step)), 'max_ms': float(np.max(per_step)), 'sources': n_local})
-    launches_per_step = (1 + len(segs)) if n_local else 0        # plan_build + one render per time segment (+ normalise)
+    launches_per_step = ((1 + len(segs)) if n_local else 0) + (3 if peer is not None else 0)     # plan_build + renders (+ peer kernels)
     if not mix_mode:
         launches_per_step += n_local
 
@@ -615,12 +632,15 @@ def run_mix(ctx, name):
         'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': workload_name(name), 'sources': n_src, 'sources_per_gpu': [p['sources'] for p in per_rank],
                    'parallelism': ('one source per rank, no data-path collective' if weak else
-                                   'sources sharded round-robin over %d rank(s); per-rank mix in the render kernel; NCCL %s of the (2, N_out) '
-                                   'fp32 mix per time segment (%d segments), overlapping the next segment\'s render' % (world, collective, len(segs))),
+                                   'sources sharded round-robin over %d rank(s); per-rank mix in the render kernel; sum of the (2, N_out) fp32 '
+                                   'mixes: %s' % (world, {'peer': 'fused with the render over NVLink peer memory - every finished tile is stored '
+                                                          'into its owner rank\'s receive buffer, then signal / rank-order reduce / wait kernels (csrc/peer.cu)',
+                                                          'none': 'none (one rank)'}.get(collective, 'NCCL %s per time segment (%d segments)' % (collective, len(segs))))),
                    'value_counts': 'source-sample-pairs/s: every source contributes N_out = %d output pairs per step' % n_out,
                    'l2_policy': 'steps rotate over %d input/output set(s) of %.0f MB per rank (L2: 126 MB)' % (n_sets, set_bytes / 1e6),
-                   'kernels_per_step': 'memset, plan_build, %d x render (filter rows synthesised in-kernel)%s' % (
-                       len(segs), ', 2 x %d NCCL %s' % (len(segs), collective) if collective != 'none' else '')},
+                   'kernels_per_step': 'memset, plan_build, %d x render (filter rows synthesised by producer warps in-kernel)%s' % (
+                       len(segs), ', peer_signal, peer_reduce, peer_wait' if peer is not None else
+                       ', 2 x %d NCCL %s' % (len(segs), collective) if collective != 'none' else '')},
         'clocks': clocks.summary(), 'gpu_launches': launches_per_step * args.steps,
         'per_rank_step_ms': {'min_of_means': min(p['mean_ms'] for p in per_rank), 'median_of_means': float(np.median([p['mean_ms'] for p in per_rank])),
                              'max_of_means': max(p['mean_ms'] for p in per_rank), 'ranks': per_rank},
@@ -630,13 +650,13 @@ def run_mix(ctx, name):
     if collective != 'none':
         ms_late, _ = ctx.timed(step_late_collective, max(5, args.steps // 2), 3)
         ms_nocomm, _ = ctx.timed(lambda i: (sets[i % n_sets][0].plan(st) if sets[i % n_sets][0] else None, render_only(i)), max(5, args.steps // 2), 3)
-        line['collective'] = {'op': collective, 'bytes_per_step': int(8 * n_out), 'ms_per_step_overlapped': ms_step,
-                              'ms_per_step_one_collective_at_the_end': ms_late, 'ms_per_step_without_collective': ms_nocomm,
+        line['collective'] = {'op': collective, 'bytes_per_step': int(8 * n_out), 'ms_per_step': ms_step,
+                              'ms_per_step_with_one_nccl_all_reduce_at_the_end': ms_late, 'ms_per_step_without_exchange': ms_nocomm,
                               'exposed_ms': ms_step - ms_nocomm}
 
     # ---- parity -------------------------------------------------------------------------------------
     if mix_mode:
-        line['parity'] = mix_parity(ctx, bank, sets[0], name, mine, segs, step)
+        line['parity'] = mix_parity(ctx, bank, sets[0], name, mine, segs, step, mix_of(0))
 
     # ---- roofline of the dominant kernel (rank 0) -----------------------------------------------------
     if rank == 0 and n_local:
@@ -669,7 +689,7 @@ def run_mix(ctx, name):
         print(json.dumps(line))
 
 
-def mix_parity(ctx, bank, first_set, name, mine, segs, step):
+def mix_parity(ctx, bank, first_set, name, mine, segs, step, mix):
     """The N-GPU mix of step 0's inputs against (a) rank 0 rendering ALL sources alone in one launch over a
     window, (b) the sum of the sources rendered one by one through the non-mixing kernel (each rank its own,
     summed in float64 across ranks)."""
@@ -678,9 +698,10 @@ def mix_parity(ctx, bank, first_set, name, mine, segs, step):
     n = secs * fs
     k, n_in, n_out = bas.render_geometry(n, CHUNK, SUB, bank)
     times = np.arange(0, n_in + 1, CHUNK, dtype=np.int64)
-    job, out = first_set
-    step(0)                                              # sets[0] again: `out` now holds the reduced mix of set 0
+    job, _ = first_set
+    step(0)                                              # sets[0] again: `mix` now holds the summed mix of set 0
     ctx.barrier()
+    out = mix
     windows = [(0, 16384), (n_out // 2 // 8192 * 8192 - 5000, n_out // 2 // 8192 * 8192 + 11384), (n_out - 16384, n_out)]
     res = {'windows': windows, 'tolerance_rel_l2': 1e-6}
     # (b) per-source renders, non-mixing kernel
@@ -918,7 +939,8 @@ def main():
     ap.add_argument('--config', default='mix64', help='mix64 (default) | single | hour | stress1024, or SURVEY.md config number 2..5')
     ap.add_argument('--variant', type=lambda v: int(v, 0), default=0, help='bas_render variant (tuning)')
     ap.add_argument('--segments', type=int, default=0, help='time segments of the mix (0: distributed.MIX_SEGMENTS)')
-    ap.add_argument('--collective', default='all_reduce', choices=['all_reduce', 'reduce'])
+    ap.add_argument('--collective', default='peer', choices=['peer', 'all_reduce', 'reduce'],
+                    help='sum of the per-rank mixes: fused with the render over peer memory (default), or NCCL')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-single', action='store_true', help='skip the single_source block')
     args = ap.parse_args()

@@ -68,6 +68,11 @@ class PipelineJob(C.Structure):
 STEP_PLAN, STEP_RENDER, STEP_NORMALISE, STEP_FUSED = 1, 2, 4, 8
 
 
+class Route(C.Structure):
+    """bas_route (include/bas_b200.h)."""
+    _fields_ = [('table_dev', C.c_void_p), ('n', C.c_int), ('rank', C.c_int), ('len', C.c_longlong), ('stride', C.c_longlong)]
+
+
 class StepJob(C.Structure):
     """bas_step_job (include/bas_b200.h)."""
     _fields_ = [('n_src', C.c_int), ('C', C.c_int), ('S', C.c_int), ('K', C.c_int), ('U', C.c_int), ('mix', C.c_int),
@@ -78,7 +83,7 @@ class StepJob(C.Structure):
                 ('diffs_left_dev', C.c_void_p), ('diffs_right_dev', C.c_void_p), ('bank_pp_dev', C.c_void_p),
                 ('bank_pp2_dev', C.c_void_p), ('terms_dev', C.c_void_p), ('filt_dev', C.c_void_p), ('gains_dev', C.c_void_p),
                 ('out_dev', C.c_void_p), ('small_dev', C.c_void_p), ('workspace_dev', C.c_void_p),
-                ('workspace_bytes', C.c_longlong)]
+                ('workspace_bytes', C.c_longlong), ('route', C.POINTER(Route))]
 
 
 class BasError(RuntimeError):
@@ -113,6 +118,10 @@ def _load():
         'bas_render_fused_shape': ([i], i),
         'bas_bank2_floats': ([i, i], ll),
         'bas_render_step': ([C.POINTER(StepJob), vp], i),
+        'bas_render_routed': ([vp, ll, ll, i, ll, i, i, i, vp, vp, vp, i, vp, ll, ll, vp, ll, vp, i, vp, ll, C.POINTER(Route), vp], i),
+        'bas_peer_signal': ([vp, i, i, C.c_uint, vp], i),
+        'bas_peer_reduce': ([vp, i, ll, ll, vp, ll, ll, vp, C.c_uint, vp, i, vp, vp], i),
+        'bas_peer_wait': ([vp, i, C.c_uint, vp], i),
         'bas_render_workspace_bytes': ([], ll),
         'bas_normalise': ([vp, ll, vp, vp], i),
         'bas_peak': ([vp, ll, vp, vp], i),

@@ -641,7 +641,7 @@ class DeviceRender:
         if self.kinds_d is not None and self.kinds_d.numel() != n_src * n_pts:
             raise ValueError('az_kind must have one entry per direction')
         self.fused = bool(FUSED and (variant & 0x3f) != _cabi.RENDER_GENERIC and lib.bas_render_fused_supported(chunksize, subchunksize)
-                          and x.data_ptr() % 16 == 0 and (n_src == 1 or x.stride(0) % 4 == 0))
+                          and lib.bas_render_fused_shape(variant) and x.data_ptr() % 16 == 0 and (n_src == 1 or x.stride(0) % 4 == 0))
         self.terms = torch.empty(n_src * n_pts * 2 * _cabi.MAX_TERMS * 8, dtype=torch.uint8, device=device)
         self.filt = None if self.fused else torch.empty((n_src * n_pts, lib.bas_filter_row_pitch(dev.taps), 2),
                                                         dtype=torch.float32, device=device)
@@ -665,8 +665,10 @@ class DeviceRender:
         self.job.p_count = 0
         _cabi.check(lib.bas_render_step(C.byref(self.job), stream), 'bas_render_step')
 
-    def render(self, stream, pa, pb, out_ptr, out_stride, gains=None, accumulate=False, normalise=False):
+    def render(self, stream, pa, pb, out_ptr, out_stride, gains=None, accumulate=False, normalise=False, route=None):
+        """route (a _cabi.Route, mixing only): finished tiles go to their owner rank's receive buffer (distributed.PeerMix)."""
         job = self.job
+        job.route = C.pointer(route) if route is not None else None
         job.flags = _cabi.STEP_RENDER | self._fused_flag | (_cabi.STEP_NORMALISE if normalise else 0)
         job.p_begin, job.p_count, job.out_dev, job.out_stride = pa, pb - pa, out_ptr, out_stride
         job.gains_dev = gains.data_ptr() if gains is not None else None
@@ -724,7 +726,8 @@ def _render_pipeline(torch, dev, src, chunksize, subchunksize, elev_azim_functio
         workspace_dev=workspace.data_ptr(), workspace_bytes=workspace.numel(),
         stream_main=main.cuda_stream, stream_up=up.cuda_stream, stream_down=down.cuda_stream,
         bank_pp2_dev=dev.bank_pp2.data_ptr() if FUSED else None)
-    fused = bool(FUSED and (variant & 0x3f) != _cabi.RENDER_GENERIC and lib.bas_render_fused_supported(chunksize, subchunksize))
+    fused = bool(FUSED and (variant & 0x3f) != _cabi.RENDER_GENERIC and lib.bas_render_fused_supported(chunksize, subchunksize)
+                 and lib.bas_render_fused_shape(variant))
     phases = _phase_plan(p0, p1, n_in, chunksize, 8 * n_rows, n_src)
     cuts = (C.c_longlong * (len(phases) + 1))(*([ph[0] for ph in phases] + [p1]))
     _cabi.check(lib.bas_pipeline_upload(C.byref(job), len(phases), cuts), 'bas_pipeline_upload')

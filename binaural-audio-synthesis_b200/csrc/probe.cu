@@ -223,9 +223,9 @@ bas_probe_block_kernel(int iters, int blocks_per_iter, float* __restrict__ sink)
             const int chunk = (lane + d) & 1;                             // lanes read two different filter rows
             const float2* ra = rows + chunk * pitch + 32 * d + 32;        // taps base - 31 .. base + 31 inside the row
             const float alpha = 0.0625f * ((lane + it) & 15);
-            const u64 aa = pack2(alpha, alpha);
+            const u64 aa[1] = {pack2(alpha, alpha)};
             const float* xa = xw + (lane + 8 - d) * kXPitch;
-            block_diag(acc, ra, aa, ra, aa, pitch, xa, 0, xa, 0);
+            block_diag<1>(acc, ra, aa, ra, aa, pitch, xa, 0, xa, 0);
         }
     }
     float s = 0.f;

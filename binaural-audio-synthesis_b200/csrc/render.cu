@@ -132,8 +132,14 @@ bas_normalise_kernel(float* __restrict__ v, long long n, const float* __restrict
 static int render_common(const float* x_dev, long long x_stride, long long n_valid, int n_src, long long n_in,
                          int C, int S, int K, const float* filt_dev, const bas_term* terms_dev, const float* bank_pp2_dev, int U,
                          const float* gains_dev, long long p_begin, long long p_count, float* out_dev, long long out_stride, int mix,
-                         float* peaks_dev, int variant, void* workspace_dev, long long workspace_bytes, void* stream) {
+                         float* peaks_dev, int variant, void* workspace_dev, long long workspace_bytes, void* stream,
+                         const bas_route* route = nullptr) {
     const bool fused = filt_dev == nullptr;
+    if (route && route->n > 1) {
+        BAS_CHECK_ARG(mix == 1 && route->table_dev && route->rank >= 0 && route->rank < route->n && route->n <= 32, "route: mixing renders only, rank < n <= 32");
+        BAS_CHECK_ARG(route->len > 0 && route->len % 32 == 0 && route->stride >= route->len && route->stride % 4 == 0, "route: slice length / stride");
+        BAS_CHECK_ARG(route->len * route->n >= p_begin + p_count, "route: the slices do not cover the output");
+    }
     BAS_CHECK_ARG(x_dev && out_dev && (filt_dev || (terms_dev && bank_pp2_dev && U >= 1)), "null pointer");
     BAS_CHECK_ARG(n_src >= 1, "n_src");
     BAS_CHECK_ARG(mix == 0 || mix == 1 || mix == BAS_MIX_ACCUMULATE, "mix must be 0, 1 or BAS_MIX_ACCUMULATE");
@@ -153,14 +159,19 @@ static int render_common(const float* x_dev, long long x_stride, long long n_val
     prm.filt_src_stride = (n_in / C + 1) * (long long)prm.pitch;
     prm.gains = gains_dev; prm.p_begin = p_begin; prm.p_end = p_begin + p_count;
     prm.out = out_dev; prm.out_stride = out_stride; prm.mix = mix ? 1 : 0; prm.accumulate = mix == BAS_MIX_ACCUMULATE ? 1 : 0; prm.peaks = peaks_dev; prm.tiles = 0; prm.parts = 1; prm.tmap = 0; prm.box_rows = 0; prm.n_box = 0;
-    prm.terms = reinterpret_cast<const TermDev*>(terms_dev); prm.bank2 = bank_pp2_dev; prm.U = U;
+    prm.terms = reinterpret_cast<const TermDev*>(terms_dev); prm.bank2 = bank_pp2_dev; prm.U = U; prm.nf = 0;
+    const bool routed = route && route->n > 1;
+    prm.route_table = routed ? route->table_dev : nullptr; prm.route_n = routed ? route->n : 0; prm.route_rank = routed ? route->rank : 0;
+    prm.route_len = routed ? route->len : 1; prm.route_stride = routed ? route->stride : 0;
 
     const int base = variant & 0x3f;
     BAS_CHECK_ARG(base == BAS_RENDER_AUTO || base == BAS_RENDER_GENERIC || base == BAS_RENDER_TILED, "variant");
-    const bool tiled_ok = S == kBlk && C % kBlk == 0 && n_valid % 4 == 0 && (reinterpret_cast<uintptr_t>(x_dev) & 15) == 0 &&
+    // the tiled kernel works on 32-sample input rows: a subchunk is a whole number of rows (32, 64, ...) or half a row (16)
+    const int subs = S == kBlk / 2 ? 2 : 1;
+    const bool tiled_ok = (S % kBlk == 0 || S == kBlk / 2) && C % kBlk == 0 && n_valid % 4 == 0 && (reinterpret_cast<uintptr_t>(x_dev) & 15) == 0 &&
                           (fused || (reinterpret_cast<uintptr_t>(filt_dev) & 15) == 0) && (n_src == 1 || x_stride % 4 == 0);
     if ((base == BAS_RENDER_TILED || fused) && !tiled_ok) {
-        bas_set_error("bas_render: tiled kernel needs S == 32, 32 | C, 4 | n_valid, 16-byte aligned signals and filter rows");
+        bas_set_error("bas_render: tiled kernel needs subchunksize 16 or a multiple of 32, 32 | C, 4 | n_valid, 16-byte aligned signals and filter rows");
         return BAS_E_UNSUPPORTED;
     }
     if (base != BAS_RENDER_GENERIC && tiled_ok) {
@@ -169,7 +180,7 @@ static int render_common(const float* x_dev, long long x_stride, long long n_val
         // 28..30 parts (code n: 2^(n-1)); otherwise the shape with the lowest estimated time is taken.
         const int tw_req = (variant >> 8) & 0xff, ns_req = (variant >> 16) & 0xff, cta_req = (variant >> 24) & 0xf;
         const int parts_code = (variant >> 28) & 0x7, parts_req = parts_code ? 1 << (parts_code - 1) : 0;
-        const int mixi = (prm.mix ? 1 : 0) + (fused ? 2 : 0);
+        const int mixi = (prm.mix ? 1 : 0) + (fused ? 2 : 0) + (subs == 2 ? 4 : 0);
         const int D = (K + kBlk - 1) / kBlk;
         const long long p_base = p_begin / kBlk * kBlk;
         const bool split = (variant & BAS_RENDER_SPLIT) || (prm.mix && !(variant & BAS_RENDER_NO_SPLIT));
@@ -221,6 +232,7 @@ static int render_common(const float* x_dev, long long x_stride, long long n_val
         }
     }
     if (fused) { bas_set_error("bas_render_fused: no tile shape fits K=%d C=%d", K, C); return BAS_E_UNSUPPORTED; }
+    if (routed) { bas_set_error("bas_render: routed mixes need the tiled kernel"); return BAS_E_UNSUPPORTED; }
     const int threads = 256;
     const long long blocks = bas_ceil_div(p_count, threads);
     BAS_CHECK_ARG(blocks < 0x7fffffffLL && n_src <= 65535, "launch too large");
@@ -249,7 +261,18 @@ extern "C" int bas_render_fused(const float* x_dev, long long x_stride, long lon
                          out_dev, out_stride, mix, peaks_dev, variant, workspace_dev, workspace_bytes, stream);
 }
 
-extern "C" int bas_render_fused_supported(int C, int S) { return S == kBlk && C % kBlk == 0 ? 1 : 0; }
+extern "C" int bas_render_routed(const float* x_dev, long long x_stride, long long n_valid, int n_src, long long n_in,
+                                 int C, int S, int K, const float* filt_dev, const bas_term* terms_dev, const float* bank_pp2_dev, int U,
+                                 const float* gains_dev, long long p_begin, long long p_count, float* out_dev, long long out_stride,
+                                 float* peaks_dev, int variant, void* workspace_dev, long long workspace_bytes, const bas_route* route,
+                                 void* stream) {
+    BAS_CHECK_ARG(route, "null route");
+    BAS_CHECK_ARG(filt_dev || (terms_dev && bank_pp2_dev), "need filter rows, or plan terms and the doubled bank");
+    return render_common(x_dev, x_stride, n_valid, n_src, n_in, C, S, K, filt_dev, filt_dev ? nullptr : terms_dev, bank_pp2_dev, U, gains_dev,
+                         p_begin, p_count, out_dev, out_stride, 1, peaks_dev, variant, workspace_dev, workspace_bytes, stream, route);
+}
+
+extern "C" int bas_render_fused_supported(int C, int S) { return (S % kBlk == 0 || S == kBlk / 2) && S >= 1 && C % kBlk == 0 && C % S == 0 ? 1 : 0; }
 
 extern "C" int bas_render_fused_shape(int variant) {
     // 1 when the (TW, NS, CTAs per SM) a variant word requests is one the fused kernel is compiled for (or none is requested)

@@ -32,6 +32,12 @@ struct RenderParams {
     const float* bank2;            // polyphase bank with every phase row stored twice: [ear][row][U][2K] (+ padding)
     int U;
     int nf;                        // FUSED: filter-row buffers in shared memory (2: producers run one item ahead)
+    // routed mix (MIX kernels, several GPUs, peer.cu): a finished tile of the local mix is not stored to `out` but
+    // into the receive buffer of the rank that owns its stretch of the output, over NVLink:
+    //   route_table[owner] + (route_rank * 2 + ear) * route_stride + (p - owner * route_len)
+    float* const* route_table;     // device array of route_n peer-mapped receive buffers, or NULL
+    int route_n, route_rank;
+    long long route_len, route_stride;
 };
 
 __device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
@@ -177,12 +183,16 @@ __host__ __device__ inline size_t tile_smem_bytes(const TileGeom& g, int TW, int
     size_t staging;
     if (fused) staging = (tmap ? 1024 : (size_t)TW * g.warp_x_bytes) + (size_t)NS * fused_x_stage_bytes(g, tmap);
     else staging = tmap ? 1024 + (size_t)NS * tmap_stage_bytes(g) : (size_t)NS * g.stage_bytes + (size_t)TW * g.warp_x_bytes;
-    return kBarBytes + staging + (size_t)((C / kBlk * 4 + 15) / 16 * 16) +
+    return kBarBytes + staging + (size_t)((C / kBlk * 8 + 15) / 16 * 16) +
            (fused ? (size_t)g.f_rows * kTermsPerRow * 8 + (size_t)nf * g.f_bytes : 0) +
            (parts > 1 ? (size_t)(TW - TS) * kStripeBytes : 0) + (mix ? (size_t)TS * kStripeBytes : 0);
 }
 // FUSED shapes: TW consumer warps + TW / 2 producer warps, two input stages, and a register budget that still
 // gives the consumers their 168 registers: (4, 2, 2), (6, 2, 1), (8, 2, 1)
+// subchunksize 16 (SUBS = 2) is compiled for two shapes only (they are fused shapes as well)
+__host__ __device__ constexpr bool subs_shape_ok(int TW, int NS, int MINB) {
+    return NS == 2 && ((TW == 4 && MINB == 2) || (TW == 8 && MINB == 1));
+}
 __host__ __device__ constexpr bool fused_shape_ok(int TW, int NS, int MINB) {
     return NS == 2 && ((TW == 4 && MINB == 2) || (TW == 6 && MINB == 1) || (TW == 8 && MINB == 1));
 }
@@ -197,9 +207,14 @@ __host__ __device__ constexpr bool fused_shape_ok(int TW, int NS, int MINB) {
 // (register-reuse operand); the lane's 32 input samples sit in registers as the scalar-broadcast
 // operand.  No tap ring: 64 accumulator + 32 sample registers, and the loads and blends of the next
 // diagonal overlap the FMAs of the current one, so a block has no serial prologue.
-__device__ __forceinline__ void block_diag(u64 (&acc)[kBlk], const float2* __restrict__ ra, u64 alpha_a,
-                                           const float2* __restrict__ rb, u64 alpha_b, int pitch,
+// SUBS subchunks per 32-sample input row (subchunksize 32 / SUBS): the blend weight belongs to the INPUT
+// sample's subchunk (apply_hrtf.py:438-443), so a diagonal's tap is blended once per subchunk of the row and
+// input sample m multiplies the blend of subchunk m / (32 / SUBS).  SUBS = 1: subchunksize 32 or a multiple.
+template <int SUBS>
+__device__ __forceinline__ void block_diag(u64 (&acc)[kBlk], const float2* __restrict__ ra, const u64 (&alpha_a)[SUBS],
+                                           const float2* __restrict__ rb, const u64 (&alpha_b)[SUBS], int pitch,
                                            const float* __restrict__ xa, int ka, const float* __restrict__ xb, int kb) {
+    constexpr int SL = kBlk / SUBS;              // input samples per subchunk of a row
     // xa / xb: the lane's input row; 16-byte chunk m4 of a row sits at chunk (m4 ^ key): key = row & 7 in the
     // swizzled tensor-map layout, 0 on the padded pitch
     float x[kBlk];
@@ -212,12 +227,17 @@ __device__ __forceinline__ void block_diag(u64 (&acc)[kBlk], const float2* __res
     for (int j = 0; j < kBlk; j += 2) {          // diagonals j, j + 1 >= 0: taps (base_a + j, base_a + j + 1) in one 16-byte load
         const ulonglong2 h0 = *reinterpret_cast<const ulonglong2*>(ra + j);
         const ulonglong2 h1 = *reinterpret_cast<const ulonglong2*>(ra + pitch + j);
-        const u64 w0 = fma2(alpha_a, sub2(h1.x, h0.x), h0.x);          // H_i + alpha (H_{i+1} - H_i)   apply_hrtf.py:443
-        const u64 w1 = fma2(alpha_a, sub2(h1.y, h0.y), h0.y);
+        const u64 d0 = sub2(h1.x, h0.x), d1 = sub2(h1.y, h0.y);
+        u64 w0[SUBS], w1[SUBS];
 #pragma unroll
-        for (int m = 0; m + j < kBlk; ++m) fma2_acc(acc[m + j], pack2(x[m], x[m]), w0);
+        for (int s = 0; s < SUBS; ++s) {
+            w0[s] = fma2(alpha_a[s], d0, h0.x);                        // H_i + alpha (H_{i+1} - H_i)   apply_hrtf.py:443
+            w1[s] = fma2(alpha_a[s], d1, h0.y);
+        }
 #pragma unroll
-        for (int m = 0; m + j + 1 < kBlk; ++m) fma2_acc(acc[m + j + 1], pack2(x[m], x[m]), w1);
+        for (int m = 0; m + j < kBlk; ++m) fma2_acc(acc[m + j], pack2(x[m], x[m]), w0[m / SL]);
+#pragma unroll
+        for (int m = 0; m + j + 1 < kBlk; ++m) fma2_acc(acc[m + j + 1], pack2(x[m], x[m]), w1[m / SL]);
     }
 #pragma unroll
     for (int m4 = 0; m4 < kBlk / 4; ++m4) {      // folded block: the d = D part reads another input row
@@ -228,13 +248,18 @@ __device__ __forceinline__ void block_diag(u64 (&acc)[kBlk], const float2* __res
     for (int i = 1; i < kBlk; i += 2) {          // diagonals -i, -(i + 1): taps (base_b - i - 1, base_b - i) in one 16-byte load
         const ulonglong2 h0 = *reinterpret_cast<const ulonglong2*>(rb - i - 1);
         const ulonglong2 h1 = *reinterpret_cast<const ulonglong2*>(rb + pitch - i - 1);
-        const u64 w1 = fma2(alpha_b, sub2(h1.y, h0.y), h0.y);          // tap base_b - i
+        const u64 d0 = sub2(h1.x, h0.x), d1 = sub2(h1.y, h0.y);
+        u64 w1[SUBS];
 #pragma unroll
-        for (int m = i; m < kBlk; ++m) fma2_acc(acc[m - i], pack2(x[m], x[m]), w1);
+        for (int s = 0; s < SUBS; ++s) w1[s] = fma2(alpha_b[s], d1, h0.y);           // tap base_b - i
+#pragma unroll
+        for (int m = i; m < kBlk; ++m) fma2_acc(acc[m - i], pack2(x[m], x[m]), w1[m / SL]);
         if (i + 1 < kBlk) {
-            const u64 w0 = fma2(alpha_b, sub2(h1.x, h0.x), h0.x);      // tap base_b - i - 1
+            u64 w0[SUBS];
 #pragma unroll
-            for (int m = i + 1; m < kBlk; ++m) fma2_acc(acc[m - i - 1], pack2(x[m], x[m]), w0);
+            for (int s = 0; s < SUBS; ++s) w0[s] = fma2(alpha_b[s], d0, h0.x);       // tap base_b - i - 1
+#pragma unroll
+            for (int m = i + 1; m < kBlk; ++m) fma2_acc(acc[m - i - 1], pack2(x[m], x[m]), w0[m / SL]);
         }
     }
 }
@@ -304,7 +329,8 @@ __device__ __forceinline__ void cta_barrier(int threads) {
 // turns on the device.  Hand-over by mbarriers (full / empty per filter buffer and per input stage); the
 // producers also issue the TMA copies of the input rows.  Same terms, same order of summation: the rows
 // are bit-identical to bas_ir_synth's.
-template <int TW, bool MIX, int NS, int MINB, bool FUSED = false>
+// SUBS: subchunks per 32-sample row (see block_diag): 1 for subchunksize 32, 64, 96, ...; 2 for subchunksize 16.
+template <int TW, bool MIX, int NS, int MINB, bool FUSED = false, int SUBS = 1>
 __global__ void __launch_bounds__((FUSED ? TW + TW / 2 : TW) * 32, MINB)
 bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ workspace, const __grid_constant__ CUtensorMap xmap) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -328,7 +354,7 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
     unsigned char* after_stages = stage_base + (size_t)NS * stage_stride;
     float* xw = reinterpret_cast<float*>(after_stages + (size_t)warp * g.warp_x_bytes);          // unused on the tensor-map path
     float* alpha_tab = reinterpret_cast<float*>(after_stages + (tmap ? 0 : (size_t)TW * g.warp_x_bytes));
-    unsigned char* after_tab = reinterpret_cast<unsigned char*>(alpha_tab) + (spc * 4 + 15) / 16 * 16;
+    unsigned char* after_tab = reinterpret_cast<unsigned char*>(alpha_tab) + (spc * 8 + 15) / 16 * 16;     // room for SUBS = 2
     int2* term_tab = reinterpret_cast<int2*>(after_tab);     // FUSED: {float offset into bank2, weight bits} per (row, ear, slot)
     unsigned char* fbuf_base = after_tab + (FUSED ? (size_t)g.f_rows * kTermsPerRow * 8 : 0);       // FUSED: nf filter-row buffers
     unsigned char* after_alpha = fbuf_base + (FUSED ? (size_t)prm.nf * g.f_bytes : 0);
@@ -352,7 +378,10 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
         if (FUSED) for (int s = 0; s < 2; ++s) { mbar_init(full_f + s, PW * 32); mbar_init(empty_f + s, TW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int s = tid; s < spc; s += (TW + PW) * 32) alpha_tab[s] = (float)(s * kBlk) / (float)prm.C;      // apply_hrtf.py:442
+    // blend weight of the subchunk that starts j samples into a chunk: alpha = j / chunksize with j a multiple of
+    // the subchunksize (apply_hrtf.py:438, :442); entry i stands for samples [i, i + 1) * 32 / SUBS of the chunk
+    for (int s = tid; s < spc * SUBS; s += (TW + PW) * 32)
+        alpha_tab[s] = (float)((s * (kBlk / SUBS)) / prm.S * prm.S) / (float)prm.C;
     __syncthreads();
     // programmatic dependent launch: everything above overlapped the tail of the previous kernel in the
     // stream; the filter rows / plan terms it wrote are read only from here on
@@ -452,7 +481,6 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
         // zero: adds exactly nothing), summed in slot order like ir_synth.cu.  Every phase row is stored twice in
         // a row, so (m - adv) mod K is the plain index m + K - adv.
         constexpr int PT = PW * 32;
-        constexpr int G = 3;                                    // (row, tap) units per thread and pass: 96 loads in flight
         const int ptid = tid - TW * 32;
         const int K = prm.K, K2 = 2 * prm.K;
         for (int j = 0; j < n_items; ++j) {
@@ -475,34 +503,47 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
             }
             asm volatile("bar.sync 2, %0;" ::"r"(PT) : "memory");
             float2* fsw = reinterpret_cast<float2*>(fbuf_base + (size_t)fb * g.f_bytes);
-            // units u = row * K + tap, dealt round-robin over the producer threads; a warp's lanes share the row
-            // whenever 32 | K, so the table reads below are broadcasts
-            int row = 0, tap = ptid;
-            while (tap >= K) { tap -= K; ++row; }
-            while (row < n_rows) {
-                float v[G][kTermsPerRow];
-                int urow[G], utap[G];
+            // One ROW per producer warp at a time (rows dealt round-robin); a lane owns taps lane, lane + 32, ...
+            // and takes them two at a time: the table entry of a term is read once for both, the second load is the
+            // first address plus 128 bytes.  Software pipelined over two register buffers: the 64 loads of the next
+            // tap pair are issued before the 64 of the current pair are consumed, so that L2 requests stay in flight
+            // through the FMA phase.  The terms are summed in slot order per ear, like ir_synth.cu.
+            const int pw = warp - TW;
+            const int pairs = (K + 63) / 64;                         // tap pairs per lane and row
+            for (int row = pw; row < n_rows; row += PW) {
+                const int2* tab = term_tab + row * kTermsPerRow;
+                float2* dst = fsw + row * prm.pitch;
+                const float* b0 = prm.bank2 + lane;
+                float va[2][kTermsPerRow], vb[2][kTermsPerRow];
+                auto issue = [&](float (&v)[2][kTermsPerRow], int pr) {
+                    // taps 64 pr + lane and 64 pr + 32 + lane; past the end of the row the loads stay inside the bank's padding
+                    const float* b = b0 + 64 * pr;
 #pragma unroll
-                for (int u = 0; u < G; ++u) {
-                    urow[u] = row; utap[u] = tap;
-                    const int2* tab = term_tab + (row < n_rows ? row : n_rows - 1) * kTermsPerRow;
-                    const float* b0 = prm.bank2 + tap;
+                    for (int t = 0; t < kTermsPerRow; ++t) {
+                        const float* q = b + tab[t].x;
+                        v[0][t] = __ldg(q);
+                        v[1][t] = __ldg(q + 32);
+                    }
+                };
+                auto consume = [&](const float (&v)[2][kTermsPerRow], int pr) {
+                    float l0 = 0.f, r0 = 0.f, l1 = 0.f, r1 = 0.f;
 #pragma unroll
-                    for (int t = 0; t < kTermsPerRow; ++t) v[u][t] = __ldg(b0 + tab[t].x);
-                    tap += PT;
-                    while (tap >= K) { tap -= K; ++row; }
-                }
-#pragma unroll
-                for (int u = 0; u < G; ++u) {
-                    if (urow[u] < n_rows) {
-                        const int2* tab = term_tab + urow[u] * kTermsPerRow;
-                        float l = 0.f, r = 0.f;
-#pragma unroll
-                        for (int t = 0; t < BAS_MAX_TERMS; ++t) {
-                            l = fmaf(__int_as_float(tab[t].y), v[u][t], l);
-                            r = fmaf(__int_as_float(tab[BAS_MAX_TERMS + t].y), v[u][BAS_MAX_TERMS + t], r);
-                        }
-                        fsw[urow[u] * prm.pitch + utap[u]] = make_float2(l, r);
+                    for (int t = 0; t < BAS_MAX_TERMS; ++t) {
+                        const float wl = __int_as_float(tab[t].y), wr = __int_as_float(tab[BAS_MAX_TERMS + t].y);
+                        l0 = fmaf(wl, v[0][t], l0); r0 = fmaf(wr, v[0][BAS_MAX_TERMS + t], r0);
+                        l1 = fmaf(wl, v[1][t], l1); r1 = fmaf(wr, v[1][BAS_MAX_TERMS + t], r1);
+                    }
+                    const int m = 64 * pr + lane;
+                    if (m < K) dst[m] = make_float2(l0, r0);
+                    if (m + 32 < K) dst[m + 32] = make_float2(l1, r1);
+                };
+                issue(va, 0);
+                for (int pr = 0; pr < pairs; pr += 2) {
+                    if (pr + 1 < pairs) issue(vb, pr + 1);
+                    consume(va, pr);
+                    if (pr + 1 < pairs) {
+                        if (pr + 2 < pairs) issue(va, pr + 2);
+                        consume(vb, pr + 1);
                     }
                 }
             }
@@ -584,8 +625,12 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
 #pragma unroll 1
             for (int d = d_first; d < d_last; ++d) {
                 const float2* ra = row_of(chunk) + kBlk * d;
-                const float alpha = alpha_tab[sub];
-                u64 aa = pack2(alpha, alpha), ab = aa;
+                u64 aa[SUBS], ab[SUBS];
+#pragma unroll
+                for (int s = 0; s < SUBS; ++s) {
+                    const float alpha = alpha_tab[sub * SUBS + s];
+                    aa[s] = ab[s] = pack2(alpha, alpha);
+                }
                 const float2* rb = ra;
                 const int xrow_a = blk + g.D - d;
                 int xrow_b = xrow_a;
@@ -594,13 +639,16 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
                     int chunk_b, sub_b;
                     split_q(q_top - g.D, chunk_b, sub_b);
                     rb = row_of(chunk_b) + kBlk * g.D;
-                    const float alpha_b = alpha_tab[sub_b];
-                    ab = pack2(alpha_b, alpha_b);
+#pragma unroll
+                    for (int s = 0; s < SUBS; ++s) {
+                        const float alpha_b = alpha_tab[sub_b * SUBS + s];
+                        ab[s] = pack2(alpha_b, alpha_b);
+                    }
                 }
                 // the lane's input rows: on the padded per-warp copy, or in place in the swizzled stage
                 const float* pa = tmap ? xs + xrow_a * kBlk : xw + (xrow_a - stripe * 32) * kXPitch;
                 const float* pb_ = tmap ? xs + xrow_b * kBlk : xw + (xrow_b - stripe * 32) * kXPitch;
-                block_diag(acc, ra, aa, rb, ab, prm.pitch, pa, tmap ? (xrow_a & 7) : 0, pb_, tmap ? (xrow_b & 7) : 0);
+                block_diag<SUBS>(acc, ra, aa, rb, ab, prm.pitch, pa, tmap ? (xrow_a & 7) : 0, pb_, tmap ? (xrow_b & 7) : 0);
                 // next row down: q - 1
                 if (q_top - d - 1 < 0) { chunk = 0; sub = 0; }
                 else if (--sub < 0) { sub = spc - 1; --chunk; }
@@ -690,8 +738,18 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
                 }
             } else {
                 float* o = prm.out + (MIX ? 0 : (long long)it.src * 2 * prm.out_stride);
-                const long long off = pb - prm.p_begin;
-                if (vec_ok && pb >= prm.p_begin && pb + kBlk <= prm.p_end) {
+                long long off = pb - prm.p_begin, ostride = prm.out_stride;
+                bool vok = vec_ok;
+                if (MIX && prm.route_table != nullptr && pb >= 0) {
+                    const long long owner = pb / prm.route_len;             // 32-output blocks never straddle owners
+                    if (owner < prm.route_n) {
+                        o = prm.route_table[owner] + (long long)prm.route_rank * 2 * prm.route_stride;
+                        off = pb - owner * prm.route_len;
+                        ostride = prm.route_stride;
+                        vok = true;                                         // receive buffers are 16-byte aligned, strides multiples of 4
+                    }
+                }
+                if (vok && pb >= prm.p_begin && pb + kBlk <= prm.p_end) {
 #pragma unroll
                     for (int r4 = 0; r4 < kBlk; r4 += 4) {
                         float l[4], rr[4];
@@ -702,12 +760,12 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
                         }
                         if (MIX && prm.accumulate) {            // earlier source groups first, then this one
                             const float4 ol = *reinterpret_cast<const float4*>(o + off + r4);
-                            const float4 orr = *reinterpret_cast<const float4*>(o + prm.out_stride + off + r4);
+                            const float4 orr = *reinterpret_cast<const float4*>(o + ostride + off + r4);
                             l[0] = ol.x + l[0]; l[1] = ol.y + l[1]; l[2] = ol.z + l[2]; l[3] = ol.w + l[3];
                             rr[0] = orr.x + rr[0]; rr[1] = orr.y + rr[1]; rr[2] = orr.z + rr[2]; rr[3] = orr.w + rr[3];
                         }
                         *reinterpret_cast<float4*>(o + off + r4) = make_float4(l[0], l[1], l[2], l[3]);
-                        *reinterpret_cast<float4*>(o + prm.out_stride + off + r4) = make_float4(rr[0], rr[1], rr[2], rr[3]);
+                        *reinterpret_cast<float4*>(o + ostride + off + r4) = make_float4(rr[0], rr[1], rr[2], rr[3]);
                     }
                 } else {
 #pragma unroll
@@ -715,8 +773,8 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
                         float l, rr; unpack2(acc[r], l, rr);
                         if (!MIX) { l *= gain; rr *= gain; }
                         if (pb + r >= prm.p_begin && pb + r < prm.p_end) {
-                            if (MIX && prm.accumulate) { l = o[off + r] + l; rr = o[prm.out_stride + off + r] + rr; }
-                            o[off + r] = l; o[prm.out_stride + off + r] = rr;
+                            if (MIX && prm.accumulate) { l = o[off + r] + l; rr = o[ostride + off + r] + rr; }
+                            o[off + r] = l; o[ostride + off + r] = rr;
                         }
                     }
                 }
@@ -747,17 +805,17 @@ inline int device_sm_count() {
 }
 
 // Resident CTAs per SM this shape reaches with `parts` warps per stripe (0: does not fit).
-template <int TW, bool MIX, int NS, int MINB, bool FUSED>
+template <int TW, bool MIX, int NS, int MINB, bool FUSED, int SUBS>
 int tiled_ctas_per_sm(int K, int C, int pitch, int parts, bool tmap) {
     if (parts < 1 || TW % parts) return 0;
-    if constexpr (FUSED && !fused_shape_ok(TW, NS, MINB)) {
+    if constexpr ((FUSED && !fused_shape_ok(TW, NS, MINB)) || (SUBS > 1 && !subs_shape_ok(TW, NS, MINB))) {
         return 0;
     } else {
         const TileGeom g = tile_geom(K, C, pitch, TW / parts);
         size_t smem = tile_smem_bytes(g, TW, NS, parts, C, MIX, tmap, FUSED, 2);
         if (FUSED && smem > 227 * 1024) smem = tile_smem_bytes(g, TW, NS, parts, C, MIX, tmap, FUSED, 1);
         if (smem > 227 * 1024) return 0;
-        auto kern = bas_render_tiled_kernel<TW, MIX, NS, MINB, FUSED>;
+        auto kern = bas_render_tiled_kernel<TW, MIX, NS, MINB, FUSED, SUBS>;
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
         int per_sm = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (FUSED ? TW + TW / 2 : TW) * 32, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -765,10 +823,10 @@ int tiled_ctas_per_sm(int K, int C, int pitch, int parts, bool tmap) {
     }
 }
 
-template <int TW, bool MIX, int NS, int MINB, bool FUSED>
+template <int TW, bool MIX, int NS, int MINB, bool FUSED, int SUBS>
 int launch_tiled(RenderParams prm, int parts, bool want_split, float* workspace, long long workspace_bytes, cudaStream_t st) {
     if (parts < 1 || TW % parts) return BAS_E_UNSUPPORTED;
-    if constexpr (FUSED && !fused_shape_ok(TW, NS, MINB)) {
+    if constexpr ((FUSED && !fused_shape_ok(TW, NS, MINB)) || (SUBS > 1 && !subs_shape_ok(TW, NS, MINB))) {
         return BAS_E_UNSUPPORTED;
     } else {
     constexpr int kThreads = (FUSED ? TW + TW / 2 : TW) * 32;
@@ -784,7 +842,7 @@ int launch_tiled(RenderParams prm, int parts, bool want_split, float* workspace,
     size_t smem = tile_smem_bytes(g, TW, NS, parts, prm.C, MIX, prm.tmap != 0, FUSED, prm.nf);
     if (FUSED && smem > 227 * 1024) { prm.nf = 1; smem = tile_smem_bytes(g, TW, NS, parts, prm.C, MIX, prm.tmap != 0, FUSED, 1); }
     if (smem > 227 * 1024) return BAS_E_UNSUPPORTED;
-    auto kern = bas_render_tiled_kernel<TW, MIX, NS, MINB, FUSED>;
+    auto kern = bas_render_tiled_kernel<TW, MIX, NS, MINB, FUSED, SUBS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { bas_set_error("bas_render: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     const long long p_base = prm.p_begin / kBlk * kBlk;
@@ -816,18 +874,20 @@ int launch_tiled(RenderParams prm, int parts, bool want_split, float* workspace,
 }
 
 // One compiled tile shape: warps per CTA x pipeline stages x CTAs per SM the registers allow.
-// index = mix + 2 * fused: [0] one source per tile, [1] mixing, [2] / [3] the same with fused filter synthesis.
+// index = mix + 2 * fused + 4 * (subchunksize 16): [0] one source per tile, [1] mixing, [2] / [3] the same with
+// fused filter synthesis, [4..7] the four again for subchunksize 16.
 struct TiledShape {
     int tw, ns, minb;
-    int (*ctas_per_sm[4])(int K, int C, int pitch, int parts, bool tmap);
-    int (*launch[4])(RenderParams prm, int parts, bool want_split, float* workspace, long long workspace_bytes, cudaStream_t st);
+    int (*ctas_per_sm[8])(int K, int C, int pitch, int parts, bool tmap);
+    int (*launch[8])(RenderParams prm, int parts, bool want_split, float* workspace, long long workspace_bytes, cudaStream_t st);
 };
-#define BAS_TILED_SHAPE(TW_, NS_, MINB_)                                                                       \
-    { TW_, NS_, MINB_,                                                                                         \
-      { tiled_ctas_per_sm<TW_, false, NS_, MINB_, false>, tiled_ctas_per_sm<TW_, true, NS_, MINB_, false>,     \
-        tiled_ctas_per_sm<TW_, false, NS_, MINB_, true>, tiled_ctas_per_sm<TW_, true, NS_, MINB_, true> },     \
-      { launch_tiled<TW_, false, NS_, MINB_, false>, launch_tiled<TW_, true, NS_, MINB_, false>,               \
-        launch_tiled<TW_, false, NS_, MINB_, true>, launch_tiled<TW_, true, NS_, MINB_, true> } }
+#define BAS_TILED_FNS(FN, TW_, NS_, MINB_)                                                               \
+    { FN<TW_, false, NS_, MINB_, false, 1>, FN<TW_, true, NS_, MINB_, false, 1>,                          \
+      FN<TW_, false, NS_, MINB_, true, 1>, FN<TW_, true, NS_, MINB_, true, 1>,                            \
+      FN<TW_, false, NS_, MINB_, false, 2>, FN<TW_, true, NS_, MINB_, false, 2>,                          \
+      FN<TW_, false, NS_, MINB_, true, 2>, FN<TW_, true, NS_, MINB_, true, 2> }
+#define BAS_TILED_SHAPE(TW_, NS_, MINB_)                                                                 \
+    { TW_, NS_, MINB_, BAS_TILED_FNS(tiled_ctas_per_sm, TW_, NS_, MINB_), BAS_TILED_FNS(launch_tiled, TW_, NS_, MINB_) }
 
 // defined in render_tw4.cu / render_tw6.cu / render_tw8.cu (one translation unit per tile width, so
 // they compile in parallel)

@@ -43,7 +43,11 @@ extern "C" int bas_render_step(const bas_step_job* j, void* stream) {
     if ((j->flags & BAS_STEP_RENDER) && j->p_count > 0) {
         BasPdlScope chained((j->flags & BAS_STEP_PLAN) != 0);      // a render-only call follows whatever the caller enqueued
         int rc;
-        if (fused)
+        if (j->route && j->route->n > 1)
+            rc = bas_render_routed(j->x_dev, j->x_stride, j->n_valid, j->n_src, j->n_in, j->C, j->S, j->K, fused ? nullptr : j->filt_dev,
+                                   j->terms_dev, j->bank_pp2_dev, j->U, j->gains_dev, j->p_begin, j->p_count, j->out_dev, j->out_stride,
+                                   peaks, j->variant, j->workspace_dev, j->workspace_bytes, j->route, st);
+        else if (fused)
             rc = bas_render_fused(j->x_dev, j->x_stride, j->n_valid, j->n_src, j->n_in, j->C, j->S, j->K, j->terms_dev, j->bank_pp2_dev,
                                   j->U, j->gains_dev, j->p_begin, j->p_count, j->out_dev, j->out_stride, j->mix, peaks, j->variant,
                                   j->workspace_dev, j->workspace_bytes, st);

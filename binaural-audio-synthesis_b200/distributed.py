@@ -59,17 +59,103 @@ def mix_segments(n_out: int, n_segments: int = None):
     return list(zip(cuts[:-1], cuts[1:]))
 
 
+class PeerMix:
+    """Sum of the per-rank mixes over peer memory, fused with the render (csrc/peer.cu): symmetric buffers of
+    this rank - a receive block per writer for the slice of the output this rank owns, the full result, and the
+    flags - with every peer's mapping of them (torch.distributed._symmetric_memory is the plumbing; all
+    arithmetic and all signalling is in libbas_b200.so).  One instance per (group, output length); reusable
+    step after step.
+
+        route = peer.route                     -> DeviceRender.render(..., route=route)
+        peer.finish(stream)                    -> signal, reduce (rank order: deterministic), wait
+        peer.result[:, :n_out]                 -> the full mix on every rank
+    """
+
+    def __init__(self, n_out: int, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        from . import _cabi
+        self.torch, self._cabi = torch, _cabi
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        device = torch.device('cuda', torch.cuda.current_device())
+        n = self.world
+        self.n_out = n_out
+        self.slice_len = (-(-n_out // n) + _SEGMENT_ALIGN - 1) // _SEGMENT_ALIGN * _SEGMENT_ALIGN
+        self.stride = self.slice_len                                # floats between ear rows of a receive block
+        self.result_stride = (n_out + 3) // 4 * 4
+        recv_floats = n * 2 * self.stride
+        result_floats = 2 * self.result_stride
+        flag_words = 64 * 3                                         # arrived[n] | done[n] | counter, a cache line apart
+        self.buf = symm.empty(recv_floats + result_floats + flag_words, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        torch.cuda.synchronize()
+        dist.barrier(group)                                         # every rank's flags are zero before anyone signals
+        bases = [int(p) for p in self.handle.buffer_ptrs]
+        off_result, off_flags = 4 * recv_floats, 4 * (recv_floats + result_floats)
+
+        def table(offset):
+            return torch.tensor([b + offset for b in bases], dtype=torch.int64, device=device)
+        self._recv_ptrs = table(0)
+        self._result_ptrs = table(off_result)
+        self._arrived_ptrs = table(off_flags)
+        self._done_ptrs = table(off_flags + 256)
+        base = self.buf.data_ptr()
+        self._recv, self._arrived, self._done, self._counter = base, base + off_flags, base + off_flags + 256, base + off_flags + 512
+        self.result = self.buf[recv_floats:recv_floats + result_floats].view(2, self.result_stride)
+        self.route = _cabi.Route(table_dev=self._recv_ptrs.data_ptr(), n=n, rank=self.rank, len=self.slice_len, stride=self.stride)
+        self.epoch = 0
+
+    def zero_my_blocks(self):
+        """A rank without sources still owes every owner its (all-zero) partial slice."""
+        torch = self.torch
+        for o in range(self.world):
+            block = self.handle.get_buffer(o, (2 * self.stride,), torch.float32, self.rank * 2 * self.stride)
+            block.zero_()
+
+    def finish(self, stream):
+        """After this rank's routed render: signal, reduce this rank's slice, wait for every slice."""
+        cabi, lib = self._cabi, self._cabi.lib
+        self.epoch += 1
+        n, e = self.world, self.epoch & 0xffffffff
+        begin = self.rank * self.slice_len
+        valid = max(0, min(self.n_out, begin + self.slice_len) - begin)
+        cabi.check(lib.bas_peer_signal(self._arrived_ptrs.data_ptr(), n, self.rank, e, stream), 'bas_peer_signal')
+        cabi.check(lib.bas_peer_reduce(self._recv, n, self.stride, valid, self._result_ptrs.data_ptr(), self.result_stride, begin,
+                                       self._arrived, e, self._done_ptrs.data_ptr(), self.rank, self._counter, stream), 'bas_peer_reduce')
+        cabi.check(lib.bas_peer_wait(self._done, n, e, stream), 'bas_peer_wait')
+
+
 def _default_render(*args, **kwargs):
     from .apply_hrtf import render_sources
     return render_sources(*args, **kwargs)
 
 
+_peer_cache = {}
+
+
+def _peer_mix(n_out, group):
+    """PeerMix of (group, output length), built on first use; None where symmetric memory is unavailable."""
+    key = (id(group), n_out)
+    if key not in _peer_cache:
+        try:
+            _peer_cache[key] = PeerMix(n_out, group)
+        except Exception as e:                                  # no P2P / symmetric memory here: NCCL does the sum
+            import warnings
+            warnings.warn('peer-memory mix unavailable (%s: %s); using NCCL' % (type(e).__name__, e))
+            _peer_cache[key] = None
+    return _peer_cache[key]
+
+
 def render_mix_by_source(signals, chunksize, subchunksize, elev_azim_functions, bank, group=None,
-                         dst=None, local_render=None, normalise=True, n_segments=None):
+                         dst=None, local_render=None, normalise=True, n_segments=None, exchange='peer'):
     """Every rank passes ONLY its own sources (see shard_sources): an (n_local, N) array (host or CUDA)
-    and one trajectory per local source.  Returns the global mix (2, N_out): on every rank
-    (all_reduce) when dst is None, else only on rank `dst` (reduce; other ranks get None).  The sum
-    over a rank's own sources is deterministic; the sum over ranks is NCCL's."""
+    and one trajectory per local source.  Returns the global mix (2, N_out): on every rank when dst is
+    None, else only on rank `dst` (other ranks get None).
+    exchange='peer' (default): the sum over ranks is fused with the render over NVLink peer memory
+    (PeerMix; deterministic rank-order sum); exchange='nccl': one NCCL all_reduce / reduce after the
+    last render.  The sum over a rank's own sources is deterministic either way."""
     import torch
     import torch.distributed as dist
     if local_render is not None:
@@ -89,7 +175,17 @@ def render_mix_by_source(signals, chunksize, subchunksize, elev_azim_functions, 
     stride = (n_out + 3) // 4 * 4
     main = torch.cuda.current_stream()
     mix = torch.zeros((2, stride), dtype=torch.float32, device=torch_dev)
-    segs = mix_segments(n_out, n_segments)
+    peer = _peer_mix(n_out, group) if exchange == 'peer' and dist.get_world_size(group) > 1 else None
+    if exchange == 'peer' and dist.get_world_size(group) > 1:
+        # all ranks must take the same path
+        ok = torch.tensor([1 if peer is not None else 0], dtype=torch.int32, device=torch_dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if not int(ok):
+            peer = None
+    host_input = n_local and not (isinstance(signals, torch.Tensor) and signals.is_cuda)
+    # time segments: a host input is uploaded slice by slice ahead of the segment that needs it; device-resident
+    # inputs render in one launch
+    segs = mix_segments(n_out, n_segments if (n_segments or host_input) else 1)
     job = None
     uploaded = {}
     if n_local:
@@ -131,22 +227,20 @@ def render_mix_by_source(signals, chunksize, subchunksize, elev_azim_functions, 
         job.plan(main.cuda_stream)
 
     def one_pass(gains):
-        works = []
         for i, (pa, pb) in enumerate(segs):
             if job is not None:
                 if i in uploaded:
                     main.wait_event(uploaded[i])
-                job.render(main.cuda_stream, pa, pb, mix.data_ptr() + 4 * pa, stride, gains=gains)
-            # the collective is ordered after the render just enqueued and runs on NCCL's own stream:
-            # the next segment's render does not wait for it.  One call per ear row (contiguous slices).
-            for ear in range(2):
-                piece = mix[ear, pa:pb]
-                if dst is None:
-                    works.append(dist.all_reduce(piece, op=dist.ReduceOp.SUM, group=group, async_op=True))
-                else:
-                    works.append(dist.reduce(piece, dst=dst, op=dist.ReduceOp.SUM, group=group, async_op=True))
-        for w in works:
-            w.wait()                                        # main stream waits; the host does not
+                job.render(main.cuda_stream, pa, pb, mix.data_ptr() + 4 * pa, stride, gains=gains,
+                           route=peer.route if peer is not None else None)
+        if peer is not None:
+            if job is None:
+                peer.zero_my_blocks()
+            peer.finish(main.cuda_stream)                   # signal, rank-order sum of this rank's slice, wait for all slices
+        elif dst is None:
+            dist.all_reduce(mix, op=dist.ReduceOp.SUM, group=group)
+        else:
+            dist.reduce(mix, dst=dst, op=dist.ReduceOp.SUM, group=group)
 
     one_pass(None)
     # ---- status, peaks, and the rare second pass of apply_hrtf.py:462-464 (see render_sources) ---------
@@ -170,7 +264,7 @@ def render_mix_by_source(signals, chunksize, subchunksize, elev_azim_functions, 
             else:
                 mix.zero_()
             one_pass(gains)
-    result = mix[:, :n_out]
+    result = peer.result[:, :n_out].clone() if peer is not None else mix[:, :n_out]
     if dst is None or rank == dst:
         return result
     return None

@@ -194,6 +194,37 @@ int bas_render_fused_supported(int C, int S);
 int bas_render_fused_shape(int variant);      /* 1: the tile shape `variant` requests is compiled for the fused kernel */
 long long bas_bank2_floats(int U, int K);
 
+/* ---- by-source sharding over several GPUs: the per-rank mixes summed over peer memory ----
+ * The reference is single-process; a mix of many sources is the sum of independent make_signal_move_2d calls
+ * (apply_hrtf.py:356-466), so sources shard over GPUs and the (2, N_out) per-rank mixes must be added.  Here
+ * the addition is fused with the render: the output is cut into n slices of `len` samples, slice o owned by rank
+ * o; bas_render_routed is bas_render(mix = 1) / bas_render_fused whose epilogue stores every finished tile into the
+ * OWNER's receive buffer over NVLink (table_dev[o], peer-mapped, laid out [writer rank][ear][stride]) while the
+ * other tiles are still being computed.  Then, on every rank, in stream order:
+ *   bas_peer_signal(arrived_ptrs, n, rank, epoch)   "my tiles have landed": one release-store per peer
+ *   bas_peer_reduce(...)                            waits for all n writers, sums their slices in rank order
+ *                                                   (deterministic), stores the sum into every rank's result
+ *                                                   buffer, and its last CTA signals "slice written" to every peer
+ *   bas_peer_wait(done_flags, n, epoch)             all n slices of the full mix are in this rank's result buffer
+ * epoch counts steps (any value that increases by one per step).  Flags, receive and result buffers are the
+ * caller's (symmetric allocations; flags and counter zeroed once); every wait is bounded by elapsed time. */
+typedef struct bas_route {
+    float* const* table_dev;      /* device array: receive buffer of every rank (peer-mapped pointers) */
+    int n, rank;                  /* ranks; this rank */
+    long long len;                /* output samples per slice (multiple of 32); n * len >= N_out */
+    long long stride;             /* floats between the ear rows of a receive block (>= len, multiple of 4) */
+} bas_route;
+int bas_render_routed(const float* x_dev, long long x_stride, long long n_valid, int n_src, long long n_in,
+                      int C, int S, int K, const float* filt_dev, const bas_term* terms_dev, const float* bank_pp2_dev, int U,
+                      const float* gains_dev, long long p_begin, long long p_count, float* out_dev, long long out_stride,
+                      float* peaks_dev, int variant, void* workspace_dev, long long workspace_bytes, const bas_route* route,
+                      void* stream);
+int bas_peer_signal(unsigned* const* flag_ptrs_dev, int n, int slot, unsigned epoch, void* stream);
+int bas_peer_reduce(const float* recv_dev, int n, long long stride, long long valid, float* const* result_ptrs_dev,
+                    long long result_stride, long long slice_begin, const unsigned* arrived_dev, unsigned epoch,
+                    unsigned* const* done_ptrs_dev, int rank, unsigned* counter_dev, void* stream);
+int bas_peer_wait(const unsigned* flags_dev, int n, unsigned epoch, void* stream);
+
 /* ---- one render step as one call: apply_hrtf.py:429-435 feeding :438-453 and :459-464 ----------
  * bas_render_step enqueues, on `stream`: [BAS_STEP_PLAN] one memset of small_dev, bas_plan_build for the
  * n_src x (n_in/C + 1) directions, and (unless BAS_STEP_FUSED) bas_ir_synth into filt_dev;
@@ -232,6 +263,7 @@ typedef struct bas_step_job {
     int32_t* small_dev;           /* 2 + n_src words: status pair (bas_plan_build), then per-source peaks */
     void* workspace_dev;          /* bas_render workspace (may be NULL) */
     long long workspace_bytes;
+    const bas_route* route;       /* mixing over several GPUs: route finished tiles to their owners (or NULL) */
 } bas_step_job;
 int bas_render_step(const bas_step_job* job, void* stream);
 

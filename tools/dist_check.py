@@ -26,12 +26,35 @@ sig = np.stack([bench.pink_noise(n, 100 + s) for s in range(n_src)])
 sig[3] *= 60.0                                     # one source that peaks above 1 and is normalised on its own
 trajs = [bench.lissajous(s) for s in range(n_src)]
 mine = bas.distributed.shard_sources(n_src, rank, world)
-mix = bas.distributed.render_mix_by_source(sig[mine], 512, 32, [trajs[s] for s in mine], bank)
-torch.cuda.synchronize()
+ref = bas.render_sources(sig, 512, 32, trajs, bank, mix=True) if rank == 0 else None
+for exchange in ('peer', 'nccl'):
+    # twice: the second call re-uses the symmetric buffers and flags of the first (epochs advance)
+    for rep in range(2):
+        mix = bas.distributed.render_mix_by_source(sig[mine], 512, 32, [trajs[s] for s in mine], bank, exchange=exchange)
+    torch.cuda.synchronize()
+    every = [None] * world
+    dist.all_gather_object(every, float(mix.double().abs().sum()))
+    if rank == 0:
+        out['by_source_%s_rel_l2_vs_one_gpu' % exchange] = rel(mix.cpu().numpy(), ref.astype(np.float64))
+        out['by_source_%s_same_on_every_rank' % exchange] = bool(max(every) == min(every))
+        out['by_source_shape'] = list(mix.shape)
+# device-resident signals, result only on rank 1 (dst), and a rank count that leaves rank world-1 without sources
+few = min(world - 1, 3) if world > 1 else 1
+mine_few = bas.distributed.shard_sources(few, rank, world)
+xd = torch.from_numpy(sig[mine_few]).cuda() if mine_few else torch.zeros((0, n), dtype=torch.float32, device='cuda')
+mix = bas.distributed.render_mix_by_source(xd, 512, 32, [trajs[s] for s in mine_few], bank, dst=world - 1)
+if rank == world - 1:
+    out_dst = mix.cpu().numpy()
+    dist.send(torch.from_numpy(out_dst).cuda(), dst=0) if world > 1 else None
 if rank == 0:
-    ref = bas.render_sources(sig, 512, 32, trajs, bank, mix=True)
-    out['by_source_rel_l2_vs_one_gpu'] = rel(mix.cpu().numpy(), ref.astype(np.float64))
-    out['by_source_shape'] = list(mix.shape)
+    ref_few = bas.render_sources(sig[:few], 512, 32, trajs[:few], bank, mix=True)
+    if world > 1:
+        got = torch.empty((2, ref_few.shape[1]), dtype=torch.float32, device='cuda')
+        dist.recv(got, src=world - 1)
+        got = got.cpu().numpy()
+    else:
+        got = out_dst
+    out['by_source_sourceless_rank_rel_l2'] = rel(got, ref_few.astype(np.float64))
 
 # ---- by time (config 4) ----
 x = 30.0 * bench.pink_noise(20 * 44100 + 123, 7)   # peaks above 1: exercises the global normalisation
@@ -42,7 +65,8 @@ if rank == 0:
     out['by_time_rel_l2_vs_one_gpu'] = rel(full, ref.astype(np.float64))
     out['by_time_peak'] = float(np.abs(full).max())
     out['by_time_shape'] = list(full.shape)
-    ok = out['by_source_rel_l2_vs_one_gpu'] < 1e-6 and out['by_time_rel_l2_vs_one_gpu'] < 1e-6 and abs(out['by_time_peak'] - 1) < 1e-6
+    ok = (out['by_source_peer_rel_l2_vs_one_gpu'] < 1e-6 and out['by_source_nccl_rel_l2_vs_one_gpu'] < 1e-6 and out['by_source_peer_same_on_every_rank'] and
+          out['by_source_sourceless_rank_rel_l2'] < 1e-6 and out['by_time_rel_l2_vs_one_gpu'] < 1e-6 and abs(out['by_time_peak'] - 1) < 1e-6)
     out['world'] = world
     out['ok'] = bool(ok)
     print(json.dumps(out))
