@@ -617,8 +617,18 @@ def _phase_plan(p0: int, p1: int, n_in: int, chunksize: int, out_bytes_per_sampl
     return phases
 
 
-FUSED = True                     # let the render kernel synthesise its filter rows (bas_render_fused) where it can;
-                                 # False: bas_ir_synth writes filter rows to HBM first (same rows, bit for bit)
+# Filter rows: synthesised inside the render kernel by its producer warps (bas_render_fused), or written to HBM
+# first by a separate bas_ir_synth launch (the two-kernel path) - the same rows, bit for bit.  'auto' fuses where
+# it measures faster on B200: up to FUSED_MAX_TAPS taps the producers keep pace with the FIR
+# blocks well enough to win (64 sources mixed at K = 256: 68.6 against 79.9 us per source); at K = 512 the gathers
+# double while the producers' registers do not, and the two-kernel path is ahead.  True / False force either.
+FUSED = 'auto'
+FUSED_MAX_TAPS = 384
+
+
+def _want_fused(taps: int) -> bool:
+    return bool(FUSED) if FUSED in (True, False) else taps <= FUSED_MAX_TAPS
+
 
 
 class DeviceRender:
@@ -640,7 +650,7 @@ class DeviceRender:
             np.ascontiguousarray(kinds, dtype=np.uint8).reshape(-1)).to(device)
         if self.kinds_d is not None and self.kinds_d.numel() != n_src * n_pts:
             raise ValueError('az_kind must have one entry per direction')
-        self.fused = bool(FUSED and (variant & 0x3f) != _cabi.RENDER_GENERIC and lib.bas_render_fused_supported(chunksize, subchunksize)
+        self.fused = bool(_want_fused(dev.taps) and (variant & 0x3f) != _cabi.RENDER_GENERIC and lib.bas_render_fused_supported(chunksize, subchunksize)
                           and lib.bas_render_fused_shape(variant) and x.data_ptr() % 16 == 0 and (n_src == 1 or x.stride(0) % 4 == 0))
         self.terms = torch.empty(n_src * n_pts * 2 * _cabi.MAX_TERMS * 8, dtype=torch.uint8, device=device)
         self.filt = None if self.fused else torch.empty((n_src * n_pts, lib.bas_filter_row_pitch(dev.taps), 2),
@@ -725,8 +735,8 @@ def _render_pipeline(torch, dev, src, chunksize, subchunksize, elev_azim_functio
         small_host=small.data_ptr(), arena_dev=arena.data_ptr(), arena_bytes=arena.numel(),
         workspace_dev=workspace.data_ptr(), workspace_bytes=workspace.numel(),
         stream_main=main.cuda_stream, stream_up=up.cuda_stream, stream_down=down.cuda_stream,
-        bank_pp2_dev=dev.bank_pp2.data_ptr() if FUSED else None)
-    fused = bool(FUSED and (variant & 0x3f) != _cabi.RENDER_GENERIC and lib.bas_render_fused_supported(chunksize, subchunksize)
+        bank_pp2_dev=dev.bank_pp2.data_ptr() if _want_fused(k) else None)
+    fused = bool(_want_fused(k) and (variant & 0x3f) != _cabi.RENDER_GENERIC and lib.bas_render_fused_supported(chunksize, subchunksize)
                  and lib.bas_render_fused_shape(variant))
     phases = _phase_plan(p0, p1, n_in, chunksize, 8 * n_rows, n_src)
     cuts = (C.c_longlong * (len(phases) + 1))(*([ph[0] for ph in phases] + [p1]))

@@ -187,14 +187,15 @@ __host__ __device__ inline size_t tile_smem_bytes(const TileGeom& g, int TW, int
            (fused ? (size_t)g.f_rows * kTermsPerRow * 8 + (size_t)nf * g.f_bytes : 0) +
            (parts > 1 ? (size_t)(TW - TS) * kStripeBytes : 0) + (mix ? (size_t)TS * kStripeBytes : 0);
 }
-// FUSED shapes: TW consumer warps + TW / 2 producer warps, two input stages, and a register budget that still
-// gives the consumers their 168 registers: (4, 2, 2), (6, 2, 1), (8, 2, 1)
+// FUSED shapes: TW consumer warps + TW producer warps (whole warpgroups of four, as setmaxnreg wants), two input
+// stages, 16 warps per SM launched at 128 registers and re-balanced to 168 (consumers) / 88 (producers):
+// (4, 2, 2) and (8, 2, 1)
 // subchunksize 16 (SUBS = 2) is compiled for two shapes only (they are fused shapes as well)
 __host__ __device__ constexpr bool subs_shape_ok(int TW, int NS, int MINB) {
     return NS == 2 && ((TW == 4 && MINB == 2) || (TW == 8 && MINB == 1));
 }
 __host__ __device__ constexpr bool fused_shape_ok(int TW, int NS, int MINB) {
-    return NS == 2 && ((TW == 4 && MINB == 2) || (TW == 6 && MINB == 1) || (TW == 8 && MINB == 1));
+    return NS == 2 && ((TW == 4 && MINB == 2) || (TW == 8 && MINB == 1));
 }
 
 // One 32x32 block, visited diagonal by diagonal:  acc[r] += x_sel[m] * tap(r - m)  for r, m = 0..31 with
@@ -331,12 +332,12 @@ __device__ __forceinline__ void cta_barrier(int threads) {
 // are bit-identical to bas_ir_synth's.
 // SUBS: subchunks per 32-sample row (see block_diag): 1 for subchunksize 32, 64, 96, ...; 2 for subchunksize 16.
 template <int TW, bool MIX, int NS, int MINB, bool FUSED = false, int SUBS = 1>
-__global__ void __launch_bounds__((FUSED ? TW + TW / 2 : TW) * 32, MINB)
+__global__ void __launch_bounds__((FUSED ? 2 * TW : TW) * 32, MINB)
 bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ workspace, const __grid_constant__ CUtensorMap xmap) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int P = prm.parts, TS = TW / P;
     const TileGeom g = tile_geom(prm.K, prm.C, prm.pitch, TS);
-    constexpr int PW = FUSED ? TW / 2 : 0;                // producer warps
+    constexpr int PW = FUSED ? TW : 0;                    // producer warps
     u64* full_bar = reinterpret_cast<u64*>(smem);              // [NS]
     u64* empty_bar = full_bar + NS;                       // [NS]
     u64* full_f = empty_bar + NS;                         // [2]  FUSED: filter buffer written / ...
@@ -473,6 +474,11 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
         __syncwarp();
     };
 
+    if (FUSED) {
+        // 16 warps per SM were launched with 128 registers each; the FIR blocks need 168, the gathers get by with 88
+        if (warp >= TW) asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+    }
     if (FUSED && warp >= TW) {
         // =========================== producer warps (FUSED) ===========================================
         // For every item, in order: the TMA copies of its input rows into stage j % NS (first producer warp), then its
@@ -505,46 +511,34 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
             float2* fsw = reinterpret_cast<float2*>(fbuf_base + (size_t)fb * g.f_bytes);
             // One ROW per producer warp at a time (rows dealt round-robin); a lane owns taps lane, lane + 32, ...
             // and takes them two at a time: the table entry of a term is read once for both, the second load is the
-            // first address plus 128 bytes.  Software pipelined over two register buffers: the 64 loads of the next
-            // tap pair are issued before the 64 of the current pair are consumed, so that L2 requests stay in flight
-            // through the FMA phase.  The terms are summed in slot order per ear, like ir_synth.cu.
+            // first address plus 128 bytes.  The terms are summed in slot order per ear, like ir_synth.cu.
             const int pw = warp - TW;
             const int pairs = (K + 63) / 64;                         // tap pairs per lane and row
             for (int row = pw; row < n_rows; row += PW) {
                 const int2* tab = term_tab + row * kTermsPerRow;
                 float2* dst = fsw + row * prm.pitch;
                 const float* b0 = prm.bank2 + lane;
-                float va[2][kTermsPerRow], vb[2][kTermsPerRow];
-                auto issue = [&](float (&v)[2][kTermsPerRow], int pr) {
+                // 64 loads in flight per lane; the second producer warp of the scheduler is in its FMA phase meanwhile
+                for (int pr = 0; pr < pairs; ++pr) {
                     // taps 64 pr + lane and 64 pr + 32 + lane; past the end of the row the loads stay inside the bank's padding
                     const float* b = b0 + 64 * pr;
+                    float v0[kTermsPerRow], v1[kTermsPerRow];
 #pragma unroll
                     for (int t = 0; t < kTermsPerRow; ++t) {
                         const float* q = b + tab[t].x;
-                        v[0][t] = __ldg(q);
-                        v[1][t] = __ldg(q + 32);
+                        v0[t] = __ldg(q);
+                        v1[t] = __ldg(q + 32);
                     }
-                };
-                auto consume = [&](const float (&v)[2][kTermsPerRow], int pr) {
                     float l0 = 0.f, r0 = 0.f, l1 = 0.f, r1 = 0.f;
 #pragma unroll
                     for (int t = 0; t < BAS_MAX_TERMS; ++t) {
                         const float wl = __int_as_float(tab[t].y), wr = __int_as_float(tab[BAS_MAX_TERMS + t].y);
-                        l0 = fmaf(wl, v[0][t], l0); r0 = fmaf(wr, v[0][BAS_MAX_TERMS + t], r0);
-                        l1 = fmaf(wl, v[1][t], l1); r1 = fmaf(wr, v[1][BAS_MAX_TERMS + t], r1);
+                        l0 = fmaf(wl, v0[t], l0); r0 = fmaf(wr, v0[BAS_MAX_TERMS + t], r0);
+                        l1 = fmaf(wl, v1[t], l1); r1 = fmaf(wr, v1[BAS_MAX_TERMS + t], r1);
                     }
                     const int m = 64 * pr + lane;
                     if (m < K) dst[m] = make_float2(l0, r0);
                     if (m + 32 < K) dst[m + 32] = make_float2(l1, r1);
-                };
-                issue(va, 0);
-                for (int pr = 0; pr < pairs; pr += 2) {
-                    if (pr + 1 < pairs) issue(vb, pr + 1);
-                    consume(va, pr);
-                    if (pr + 1 < pairs) {
-                        if (pr + 2 < pairs) issue(va, pr + 2);
-                        consume(vb, pr + 1);
-                    }
                 }
             }
             const int pad = prm.pitch - K;                           // zero padding taps K .. pitch - 1 of every row
@@ -818,7 +812,7 @@ int tiled_ctas_per_sm(int K, int C, int pitch, int parts, bool tmap) {
         auto kern = bas_render_tiled_kernel<TW, MIX, NS, MINB, FUSED, SUBS>;
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (FUSED ? TW + TW / 2 : TW) * 32, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (FUSED ? 2 * TW : TW) * 32, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
         return per_sm;
     }
 }
@@ -829,7 +823,7 @@ int launch_tiled(RenderParams prm, int parts, bool want_split, float* workspace,
     if constexpr ((FUSED && !fused_shape_ok(TW, NS, MINB)) || (SUBS > 1 && !subs_shape_ok(TW, NS, MINB))) {
         return BAS_E_UNSUPPORTED;
     } else {
-    constexpr int kThreads = (FUSED ? TW + TW / 2 : TW) * 32;
+    constexpr int kThreads = (FUSED ? 2 * TW : TW) * 32;
     const int TS = TW / parts;
     const TileGeom g = tile_geom(prm.K, prm.C, prm.pitch, TS);
     // input rows by tensor-map TMA when the signal allows it (whole 32-sample rows, 16-byte aligned)

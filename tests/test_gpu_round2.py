@@ -168,3 +168,38 @@ def test_bank_cache_follows_the_callers_arrays(bas, synth_bank):
     bank.irs_left *= 2.0
     b = bas.interpolate_2d(bank, 0.2, 1.0)
     assert np.allclose(b[0], 2.0 * a[0], rtol=1e-6) and np.array_equal(b[1], a[1])
+
+
+@pytest.mark.parametrize('sub', [16, 64, 128, 256])
+@pytest.mark.parametrize('fused', [True, False])
+def test_tiled_kernel_takes_subchunksize_16_and_multiples_of_32(bas, oracle, synth_bank, sub, fused, monkeypatch):
+    """the reference's docstring recommends subchunksize 16 or 32 (apply_hrtf.py:380-381).  The
+    tiled kernel (requested explicitly: BAS_RENDER_TILED fails where it does not apply) renders subchunksize 16
+    - two blend weights per 32-sample input row - and every multiple of 32 that divides the chunk, fused and not,
+    one source per tile and mixing, against the oracle."""
+    ah = bas.apply_hrtf
+    monkeypatch.setattr(ah, 'FUSED', fused)
+    rng = np.random.default_rng(50 + sub)
+    n = 9000
+    x = (0.05 * rng.standard_normal((3, n))).astype(np.float32)
+    trajs = [_traj(s) for s in range(3)]
+    want = np.stack([oracle.make_signal_move_2d(x[s], 256, sub, trajs[s], synth_bank).T for s in range(3)])
+    for variant in (bas._cabi.RENDER_TILED, bas._cabi.render_variant(8, 2, 1, 1), bas._cabi.render_variant(4, 2, 2, 2)):
+        got = bas.render_sources(x, 256, sub, trajs, synth_bank, normalise=False, variant=variant, return_device=True).cpu().numpy()
+        close(got, want)
+        mix = bas.render_sources(x, 256, sub, trajs, synth_bank, mix=True, normalise=False, variant=variant, return_device=True).cpu().numpy()
+        close(mix, want.sum(axis=0))
+    # through the drop-in call (host arrays, pipeline): the library's own choice
+    bas.apply_hrtf.PROGRESS = False
+    got = bas.make_signal_move_2d(x[0], 256, sub, trajs[0], synth_bank)
+    close(got.T, oracle.make_signal_move_2d(x[0], 256, sub, trajs[0], synth_bank).T)
+
+
+def test_subchunksize_8_still_renders_through_the_generic_kernel(bas, oracle, synth_bank):
+    rng = np.random.default_rng(58)
+    x = (0.05 * rng.standard_normal(3000)).astype(np.float32)
+    bas.apply_hrtf.PROGRESS = False
+    got = bas.make_signal_move_2d(x, 64, 8, _traj(1), synth_bank)
+    close(got, oracle.make_signal_move_2d(x, 64, 8, _traj(1), synth_bank))
+    with pytest.raises(bas.BasError):
+        bas.render_sources(x[None], 64, 8, [_traj(1)], synth_bank, variant=bas._cabi.RENDER_TILED, return_device=True)

@@ -44,7 +44,7 @@ def timed(fn, reps=8):
 
 res = {}
 shapes = [(0, 0, 0)] + list(cabi.TILED_SHAPES)
-FUSED_SHAPES = {(0, 0, 0), (4, 2, 2), (6, 2, 1), (8, 2, 1)}
+FUSED_SHAPES = {(0, 0, 0), (4, 2, 2), (8, 2, 1)}
 for fused in (True, False):
     ah.FUSED = fused
     for tw, ns, ctas in shapes:
