@@ -183,16 +183,16 @@ def test_tiled_kernel_takes_subchunksize_16_and_multiples_of_32(bas, oracle, syn
     n = 9000
     x = (0.05 * rng.standard_normal((3, n))).astype(np.float32)
     trajs = [_traj(s) for s in range(3)]
-    want = np.stack([oracle.make_signal_move_2d(x[s], 256, sub, trajs[s], synth_bank).T for s in range(3)])
+    want = np.stack([oracle.make_signal_move_2d(x[s], 512, sub, trajs[s], synth_bank).T for s in range(3)])
     for variant in (bas._cabi.RENDER_TILED, bas._cabi.render_variant(8, 2, 1, 1), bas._cabi.render_variant(4, 2, 2, 2)):
-        got = bas.render_sources(x, 256, sub, trajs, synth_bank, normalise=False, variant=variant, return_device=True).cpu().numpy()
+        got = bas.render_sources(x, 512, sub, trajs, synth_bank, normalise=False, variant=variant, return_device=True).cpu().numpy()
         close(got, want)
-        mix = bas.render_sources(x, 256, sub, trajs, synth_bank, mix=True, normalise=False, variant=variant, return_device=True).cpu().numpy()
+        mix = bas.render_sources(x, 512, sub, trajs, synth_bank, mix=True, normalise=False, variant=variant, return_device=True).cpu().numpy()
         close(mix, want.sum(axis=0))
     # through the drop-in call (host arrays, pipeline): the library's own choice
     bas.apply_hrtf.PROGRESS = False
-    got = bas.make_signal_move_2d(x[0], 256, sub, trajs[0], synth_bank)
-    close(got.T, oracle.make_signal_move_2d(x[0], 256, sub, trajs[0], synth_bank).T)
+    got = bas.make_signal_move_2d(x[0], 512, sub, trajs[0], synth_bank)
+    close(got.T, oracle.make_signal_move_2d(x[0], 512, sub, trajs[0], synth_bank).T)
 
 
 def test_subchunksize_8_still_renders_through_the_generic_kernel(bas, oracle, synth_bank):
