@@ -218,9 +218,19 @@ def render_mix_by_source(signals, chunksize, subchunksize, elev_azim_functions, 
                 uploaded[i] = torch.cuda.Event()
                 uploaded[i].record(up)
         elev, azim, kinds = ah._directions(elev_azim_functions, n_local, n_in, chunksize)
-        elev_d = torch.as_tensor(np.asarray(elev) if not isinstance(elev, torch.Tensor) else elev, dtype=torch.float64).to(torch_dev).contiguous()
-        azim_d = torch.as_tensor(np.asarray(azim) if not isinstance(azim, torch.Tensor) else azim, dtype=torch.float64).to(torch_dev).contiguous()
-        if elev_d.numel() != n_local * (n_in // chunksize + 1) or azim_d.numel() != elev_d.numel():
+        n_dirs = n_local * (n_in // chunksize + 1)
+        if isinstance(elev, torch.Tensor) or isinstance(azim, torch.Tensor):
+            elev_d = torch.as_tensor(elev, dtype=torch.float64).to(torch_dev).contiguous()
+            azim_d = torch.as_tensor(azim, dtype=torch.float64).to(torch_dev).contiguous()
+        else:
+            # The plan kernel reads the directions IN PLACE from pinned host memory (16 B per point over PCIe): a
+            # host -> device copy would queue on the copy engine behind the signal upload enqueued above and
+            # hold the first render back until the last sample has arrived.
+            staged = ah._host_cache.pinned_bytes(torch, 'mix_dirs', 16 * n_dirs)[:16 * n_dirs].view(torch.float64)
+            staged[:n_dirs] = torch.from_numpy(np.ascontiguousarray(elev, dtype=np.float64).reshape(-1))
+            staged[n_dirs:] = torch.from_numpy(np.ascontiguousarray(azim, dtype=np.float64).reshape(-1))
+            elev_d, azim_d = staged[:n_dirs], staged[n_dirs:]
+        if elev_d.numel() != n_dirs or azim_d.numel() != n_dirs:
             raise ValueError('trajectories must give %d directions per source' % (n_in // chunksize + 1))
         job = ah.DeviceRender(torch, dev, x, n_in, chunksize, subchunksize, elev_d.reshape(-1), azim_d.reshape(-1), kinds, True,
                               ah._cabi.RENDER_AUTO)
