@@ -374,16 +374,16 @@ class Ctx:
         return out
 
 
-def traffic_of(kernel_prefix):
-    """DRAM bytes per launch of a kernel from the committed ncu --set full capture (profiles/), or None."""
-    for fname in ('r2_traffic.json', 'r1_traffic.json'):
-        path = os.path.join(ROOT, 'profiles', fname)
-        if not os.path.exists(path):
-            continue
-        tj = json.load(open(path))
-        for name, kv in tj['kernels'].items():
-            if name.startswith(kernel_prefix) and kv.get('match', kernel_prefix) == kernel_prefix:
-                return kv['dram_bytes_read'] + kv['dram_bytes_write'], 'profiles/%s (%s): %s' % (fname, tj.get('source', '?'), name)
+def traffic_of(mix):
+    """DRAM bytes per launch of the render kernel (mixing or one source per tile) from the committed ncu --set full
+    capture (profiles/r2_traffic.json), or None."""
+    path = os.path.join(ROOT, 'profiles', 'r2_traffic.json')
+    if not os.path.exists(path):
+        return None, None
+    tj = json.load(open(path))
+    for name, kv in tj['kernels'].items():
+        if name.startswith('bas_render_tiled_kernel') and bool(kv.get('mix')) == bool(mix):
+            return kv['dram_bytes_read'] + kv['dram_bytes_write'], 'profiles/r2_traffic.json (%s): %s, %s' % (kv['report'], name, kv['command'])
     return None, None
 
 
@@ -458,7 +458,7 @@ def single_source_block(ctx, bank, fs, secs, sigma, steps):
     algo = 12.0 * n_out
     useful_fma = 2.0 * k * n_in
     fma = ctx.fma_probe()
-    traffic, traffic_src = traffic_of('bas_render_tiled_kernel')
+    traffic, traffic_src = traffic_of(False)
     block = {
         'workload': workload_name('single'),
         'ms_per_step_one_at_a_time': ms_serial, 'ms_per_step_4_in_flight': ms_flight,
@@ -665,7 +665,7 @@ def run_mix(ctx, name):
         algo = (4.0 * n_local + 8.0) * n_out if mix_mode else 12.0 * n_out * n_local
         useful_fma = 2.0 * k * n_in * n_local
         fma = ctx.fma_probe()
-        traffic, traffic_src = traffic_of('bas_render_tiled_kernel_mix') if mix_mode else traffic_of('bas_render_tiled_kernel')
+        traffic, traffic_src = traffic_of(mix_mode)
         line['roofline'] = {
             'bound': 'hbm', 'kernel': 'bas_render_tiled_kernel<MIX, FUSED> (%d launches per step, one per time segment)' % len(segs),
             'achieved': algo / (ms_render * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': algo / (ms_render * 1e-3) / 1e9 / hbm_peak,

@@ -20,6 +20,7 @@ from .apply_hrtf import (                                                  # noq
     make_signal_move,
     render_sources,
     render_geometry,
+    suggest_chunk_sizes,
     evaluate_trajectory,
     plan_points_host,
 )
@@ -28,6 +29,6 @@ __all__ = [
     'load_irs_and_delaydiffs', 'delay_compensated_interpolation_with_delaydiff',
     'delay_compensated_interpolation', 'delay_compensated_interpolation_easy', 'delay_signal_float', 'interpolate_2d',
     'interpolate_2d_deg', 'interpolate_2d_batch', 'make_signal_move_2d', 'make_signal_move', 'render_sources',
-    'render_geometry', 'evaluate_trajectory', 'plan_points_host', 'sphere', 'bank_synth', 'bank_builder', 'distributed',
+    'render_geometry', 'suggest_chunk_sizes', 'evaluate_trajectory', 'plan_points_host', 'sphere', 'bank_synth', 'bank_builder', 'distributed',
     'BasError',
 ]

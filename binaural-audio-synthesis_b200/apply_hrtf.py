@@ -757,6 +757,17 @@ def _render_pipeline(torch, dev, src, chunksize, subchunksize, elev_azim_functio
         raise ValueError('need one trajectory per source')
     kinds_ptr = staged.data_ptr() + n_dirs * 16
     traj_state = [{} for _ in range(n_src)]
+    if pre is None and n_src >= 4 and len(phases) > 1:
+        # Many sources: one array evaluation per trajectory for the whole signal, before the first phase, and ONE plan
+        # launch for all boundaries.  Per-phase evaluation (below) costs a Python round trip per source and phase - more
+        # than the phases' device work for dozens of sources - while the signal upload (the long pole) runs anyway.
+        times = np.arange(0, n_in + 1, chunksize, dtype=np.int64)
+        for s, fn in enumerate(elev_azim_functions):
+            elev_h[s], azim_h[s], kinds_h[s] = evaluate_trajectory(fn, times, traj_state[s])
+        pre = True
+        phases = [(pa, pb, 0 if i == 0 else n_pts, n_pts) for i, (pa, pb, _, _) in enumerate(phases)]
+    elif pre is not None:
+        phases = [(pa, pb, 0 if i == 0 else n_pts, n_pts) for i, (pa, pb, _, _) in enumerate(phases)]
     for i, (pa, pb, pt0, pt1) in enumerate(phases):
         # the trajectory of this phase is evaluated while the signal and the earlier phases travel
         if pre is None and pt1 > pt0:
@@ -962,6 +973,29 @@ def render_sources(signals, chunksize: int, subchunksize: int, elev_azim_functio
     if mix:
         result = result[0]
     return (result, peaks_host) if return_peaks else result
+
+
+def suggest_chunk_sizes(elev_azim_function, n_samples: int, max_chunk_degrees: float = 6.0, max_subchunk_degrees: float = 0.5,
+                        chunk_sizes=(1024, 512, 256, 128), subchunk_sizes=(64, 32, 16)):
+    """The reference's "idea for the future" (apply_hrtf.py:383-385): choose chunksize and subchunksize from how fast
+    the source moves.  The trajectory is sampled every 128 samples; the pair returned is the largest chunksize whose
+    fastest chunk turns the source by at most max_chunk_degrees (one HRIR interpolation per chunk: less than half a
+    15-degree grid cell by default) and the largest subchunksize whose fastest subchunk turns it by at most
+    max_subchunk_degrees (one cross-fade step per subchunk).  Every pair this returns runs on the tiled kernel
+    (subchunksize 16, 32 or 64; chunksize a multiple of both).  One choice per call: sizes that vary inside a
+    call would no longer be the reference's algorithm."""
+    probe = 128
+    times = np.arange(0, max(int(n_samples), probe) + 1, probe, dtype=np.int64)
+    elev, azim, _ = evaluate_trajectory(elev_azim_function, times)
+    elev = np.clip(elev, -np.pi / 4, np.pi / 2)              # the renderer clamps to the grid's elevation range
+    u = np.stack([np.cos(elev) * np.cos(azim), np.cos(elev) * np.sin(azim), np.sin(elev)], axis=1)
+    if len(u) < 2:
+        return int(chunk_sizes[0]), int(subchunk_sizes[0])
+    step = np.degrees(np.arccos(np.clip((u[1:] * u[:-1]).sum(axis=1), -1.0, 1.0)))       # degrees per 128 samples
+    speed = float(np.nanmax(step)) / probe if np.isfinite(step).any() else 0.0               # degrees per sample, fastest stretch
+    chunk = next((c for c in chunk_sizes if c * speed <= max_chunk_degrees), chunk_sizes[-1])
+    sub = next((b for b in subchunk_sizes if b * speed <= max_subchunk_degrees and chunk % b == 0), subchunk_sizes[-1])
+    return int(chunk), int(sub)
 
 
 def make_signal_move_2d(in_signal, chunksize: int, subchunksize: int, elev_azim_function, irs_and_delaydiffs):

@@ -29,6 +29,15 @@ int bas_probe_clock(int packed, int blocks, int threads, int iters, float* sink_
  * ctas_per_sm (1..3) selects the register budget the block is compiled for. */
 int bas_probe_block(int ctas_per_sm, int blocks, int iters, float* sink_dev, void* stream);
 
+/* FEASIBILITY PROBE (tc_probe.cu): the chunk / subchunk FIR of make_signal_move_2d (apply_hrtf.py:431-453) for ONE source as a
+ * Toeplitz contraction on tcgen05 (kind::tf32, 3 x TF32 split, accumulators in TMEM), the Toeplitz operand addressed through
+ * overlapping shared-memory descriptors instead of being materialised.  x_dev: n_in samples (multiple of C = 512); filt_dev: the
+ * (n_in / C + 1) filter rows of bas_ir_synth(BAS_IR_ROWS); out_dev: 2 x out_stride floats, ZEROED by the caller.
+ * mode 0: correct end to end (global atomics) - accuracy; mode 1: MMAs + TMEM loads + register overlap-add, nothing stored -
+ * rate proxy; mode 2: MMAs only.  blocks: CTAs (one per SM).  K <= 258. */
+int bas_probe_tc_render(const float* x_dev, long long n_in, const float* filt_dev, int K, int C, float* out_dev,
+                        long long out_stride, long long n_out, int mode, int blocks, float* sink_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -203,3 +203,37 @@ def test_subchunksize_8_still_renders_through_the_generic_kernel(bas, oracle, sy
     close(got, oracle.make_signal_move_2d(x, 64, 8, _traj(1), synth_bank))
     with pytest.raises(bas.BasError):
         bas.render_sources(x[None], 64, 8, [_traj(1)], synth_bank, variant=bas._cabi.RENDER_TILED, return_device=True)
+
+
+def test_cli_scene_mixes_several_sources(bas, oracle, golden_bank, tmp_path):
+    """a scene description (several wav sources, each with its trajectory, gain and delay) rendered
+    into one binaural wav = the sum of the reference's make_signal_move_2d outputs of the sources."""
+    import json
+    import scipy.io
+    from scipy.io import wavfile
+    from binaural_audio_synthesis_b200 import cli
+    fs = 8000
+    rng = np.random.default_rng(77)
+    a = (0.2 * rng.standard_normal(3000)).astype(np.float32)
+    b = (0.2 * rng.standard_normal(2200)).astype(np.float32)
+    wavfile.write(str(tmp_path / 'a.wav'), fs, a)
+    wavfile.write(str(tmp_path / 'b.wav'), fs, b)
+    scipy.io.savemat(str(tmp_path / 'bank.mat'), {'irs_and_delaydiffs': {
+        'upsampling': float(golden_bank.upsampling), 'diffs_left': golden_bank.diffs_left, 'diffs_right': golden_bank.diffs_right,
+        'irs_left': golden_bank.irs_left, 'irs_right': golden_bank.irs_right}}, format='5', do_compression=False)
+    k = golden_bank.irs_left.shape[1] // golden_bank.upsampling
+    scene = {'output': str(tmp_path / 'mix.wav'), 'chunksize': 256, 'subchunksize': 32, 'samples_to_keep': k,
+             'sources': [{'wav': str(tmp_path / 'a.wav'), 'trajectory': 'circle_horizontal', 'gain': 0.5, 'period': 0.5},
+                         {'wav': str(tmp_path / 'b.wav'), 'trajectory': 'passing', 'gain': 1.0, 'delay': 0.05, 'period': 0.5}]}
+    (tmp_path / 'scene.json').write_text(json.dumps(scene))
+    assert cli.main(['--scene', str(tmp_path / 'scene.json'), '--bank', str(tmp_path / 'bank.mat')]) == 0
+    rate, got = wavfile.read(scene['output'])
+    assert rate == fs and got.dtype == np.float32
+    lead = int(round(0.05 * fs))
+    n = max(a.size, b.size + lead)
+    xa = np.zeros(n, dtype=np.float32); xa[:a.size] = 0.5 * (a / a.max())
+    xb = np.zeros(n, dtype=np.float32); xb[lead:lead + b.size] = b / b.max()
+    traj = cli.trajectories(fs, period=0.5)
+    want = (oracle.make_signal_move_2d(xa, 256, 32, traj['circle_horizontal'], golden_bank).astype(np.float64) +
+            oracle.make_signal_move_2d(xb, 256, 32, lambda t: traj['passing'](t - lead), golden_bank))
+    close(got.astype(np.float64), want)

@@ -104,3 +104,21 @@ def test_short_trajectories_just_loop(bas):
     fn = lambda t: (calls.append(np.ndim(t)), (0.0, 1e-4 * t))[1]
     bas.apply_hrtf.evaluate_trajectory(fn, TIMES[:8])
     assert calls == [0] * 8
+
+
+def test_suggest_chunk_sizes_follows_the_source_speed(bas):
+    """apply_hrtf.py:383-385, the reference's "idea for the future": faster sources get smaller chunks; every
+    suggestion is a pair the tiled kernel takes (subchunksize 16 / 32 / 64 dividing the chunksize)."""
+    from binaural_audio_synthesis_b200 import cli
+    slow = cli.trajectories(FS, period=60.0)['circle_horizontal']
+    usual = cli.trajectories(FS, period=4.0)['circle_horizontal']
+    fast = cli.trajectories(FS, period=0.25)['circle_horizontal']
+    sizes = [bas.suggest_chunk_sizes(f, 5 * FS) for f in (slow, usual, fast)]
+    assert sizes[0][0] >= sizes[1][0] >= sizes[2][0] and sizes[0][1] >= sizes[1][1] >= sizes[2][1]
+    assert sizes[2] == (128, 16) and sizes[0] == (1024, 64)
+    for c, s in sizes:
+        assert c % s == 0 and s in (16, 32, 64)
+    # the fastest stretch decides, and per-chunk rotation stays below the bound
+    c, s = bas.suggest_chunk_sizes(usual, 5 * FS, max_chunk_degrees=6.0)
+    assert c * 360.0 / (4.0 * FS) <= 6.0
+    assert bas.suggest_chunk_sizes(lambda t: (0.3, 1.0), 5 * FS) == (1024, 64)          # a source that does not move
