@@ -528,7 +528,8 @@ def run_mix(ctx, name):
     mix_mode = not weak
     collective = args.collective if (world > 1 and mix_mode) else 'none'
     peer = None
-    if collective == 'peer':
+    sharded = collective == 'peer_sharded'
+    if collective in ('peer', 'peer_sharded'):
         peer = distributed._peer_mix(n_out, None)
         ok = torch.tensor([1 if peer is not None else 0], dtype=torch.int32, device=ctx.dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
@@ -564,11 +565,13 @@ def run_mix(ctx, name):
             elif collective == 'reduce':
                 works.append(dist.reduce(piece, dst=0, async_op=True))
 
-    def step(i):
+    def step(i, replicate=None):
         job, out = sets[i % n_sets]
         works = []
         if job is not None:
             job.plan(st)
+        if peer is not None:
+            peer.begin(st)                                # sharded results: the owners have finished with the previous step
         for pa, pb in segs:
             if job is not None:
                 job.render(st, pa, pb, out.data_ptr() + 4 * pa, stride, normalise=not mix_mode, route=peer.route if peer is not None else None)
@@ -577,13 +580,16 @@ def run_mix(ctx, name):
         if peer is not None:
             if job is None:
                 peer.zero_my_blocks()
-            peer.finish(st)                               # signal, rank-order sum of this rank's slice, wait for all slices
+            # signal, rank-order sum of this rank's slice; replicated: stored on every rank, wait for all slices
+            peer.finish(st, replicate=(not sharded) if replicate is None else replicate)
         for w in works:
             w.wait()
 
     def mix_of(i):
-        """Where step i leaves the global mix."""
-        return peer.result if peer is not None else sets[i % n_sets][1]
+        """The global mix step i left behind (assembled from the ranks' slices when it was left sharded)."""
+        if peer is None:
+            return sets[i % n_sets][1]
+        return peer.gather() if sharded else peer.result
 
     def step_late_collective(i):
         """The round-1 arrangement, for comparison: one collective after the last render."""
@@ -622,7 +628,7 @@ def run_mix(ctx, name):
             assert not mix_mode or float(small[2:].view(np.float32).max()) <= 1.0
     per_rank = ctx.gather_objects({'rank': rank, 'mean_ms': float(np.mean(per_step)), 'min_ms': float(np.min(per_step)),
                                    'median_ms': float(np.median(per_step)), 'max_ms': float(np.max(per_step)), 'sources': n_local})
-    launches_per_step = ((1 + len(segs)) if n_local else 0) + (3 if peer is not None else 0)     # plan_build + renders (+ peer kernels)
+    launches_per_step = ((1 + len(segs)) if n_local else 0) + (2 if peer is not None else 0)     # plan_build + renders (+ peer kernels)
     if not mix_mode:
         launches_per_step += n_local
 
@@ -634,12 +640,17 @@ def run_mix(ctx, name):
                    'parallelism': ('one source per rank, no data-path collective' if weak else
                                    'sources sharded round-robin over %d rank(s); per-rank mix in the render kernel; sum of the (2, N_out) fp32 '
                                    'mixes: %s' % (world, {'peer': 'fused with the render over NVLink peer memory - every finished tile is stored '
-                                                          'into its owner rank\'s receive buffer, then signal / rank-order reduce / wait kernels (csrc/peer.cu)',
+                                                          'into its owner rank\'s receive buffer, then a rank-order reduce kernel per owner that stores the sum '
+                                                          'on EVERY rank (all-reduce semantics; csrc/peer.cu)',
+                                                          'peer_sharded': 'fused with the render over NVLink peer memory - every finished tile is stored into its '
+                                                          'owner rank\'s receive buffer, then a rank-order reduce kernel per owner; the summed mix is left SHARDED BY '
+                                                          'TIME over the ranks (reduce-scatter semantics; csrc/peer.cu) - collective.ms_per_step_replicated is the '
+                                                          'all-reduce form',
                                                           'none': 'none (one rank)'}.get(collective, 'NCCL %s per time segment (%d segments)' % (collective, len(segs))))),
                    'value_counts': 'source-sample-pairs/s: every source contributes N_out = %d output pairs per step' % n_out,
                    'l2_policy': 'steps rotate over %d input/output set(s) of %.0f MB per rank (L2: 126 MB)' % (n_sets, set_bytes / 1e6),
                    'kernels_per_step': 'memset, plan_build, %d x render (filter rows synthesised by producer warps in-kernel)%s' % (
-                       len(segs), ', peer_signal, peer_reduce, peer_wait' if peer is not None else
+                       len(segs), ', peer_reduce (+ peer_wait)' if peer is not None else
                        ', 2 x %d NCCL %s' % (len(segs), collective) if collective != 'none' else '')},
         'clocks': clocks.summary(), 'gpu_launches': launches_per_step * args.steps,
         'per_rank_step_ms': {'min_of_means': min(p['mean_ms'] for p in per_rank), 'median_of_means': float(np.median([p['mean_ms'] for p in per_rank])),
@@ -650,13 +661,18 @@ def run_mix(ctx, name):
     if collective != 'none':
         ms_late, _ = ctx.timed(step_late_collective, max(5, args.steps // 2), 3)
         ms_nocomm, _ = ctx.timed(lambda i: (sets[i % n_sets][0].plan(st) if sets[i % n_sets][0] else None, render_only(i)), max(5, args.steps // 2), 3)
-        line['collective'] = {'op': collective, 'bytes_per_step': int(8 * n_out), 'ms_per_step': ms_step,
+        ms_repl = None
+        if peer is not None:
+            ms_repl, _ = ctx.timed(lambda i: step(i, replicate=True), max(5, args.steps // 2), 3)
+            if sharded:
+                step(0)                                  # leave the buffers in the default (sharded) state
+        line['collective'] = {'op': collective, 'bytes_per_step': int(8 * n_out), 'ms_per_step': ms_step, 'ms_per_step_replicated': ms_repl,
                               'ms_per_step_with_one_nccl_all_reduce_at_the_end': ms_late, 'ms_per_step_without_exchange': ms_nocomm,
                               'exposed_ms': ms_step - ms_nocomm}
 
     # ---- parity -------------------------------------------------------------------------------------
     if mix_mode:
-        line['parity'] = mix_parity(ctx, bank, sets[0], name, mine, segs, step, mix_of(0))
+        line['parity'] = mix_parity(ctx, bank, sets[0], name, mine, segs, step, mix_of)
 
     # ---- roofline of the dominant kernel (rank 0) -----------------------------------------------------
     if rank == 0 and n_local:
@@ -699,9 +715,9 @@ def mix_parity(ctx, bank, first_set, name, mine, segs, step, mix):
     k, n_in, n_out = bas.render_geometry(n, CHUNK, SUB, bank)
     times = np.arange(0, n_in + 1, CHUNK, dtype=np.int64)
     job, _ = first_set
-    step(0)                                              # sets[0] again: `mix` now holds the summed mix of set 0
+    step(0)                                              # sets[0] again
     ctx.barrier()
-    out = mix
+    out = mix(0)                                         # the summed mix of set 0
     windows = [(0, 16384), (n_out // 2 // 8192 * 8192 - 5000, n_out // 2 // 8192 * 8192 + 11384), (n_out - 16384, n_out)]
     res = {'windows': windows, 'tolerance_rel_l2': 1e-6}
     # (b) per-source renders, non-mixing kernel
@@ -939,8 +955,9 @@ def main():
     ap.add_argument('--config', default='mix64', help='mix64 (default) | single | hour | stress1024, or SURVEY.md config number 2..5')
     ap.add_argument('--variant', type=lambda v: int(v, 0), default=0, help='bas_render variant (tuning)')
     ap.add_argument('--segments', type=int, default=0, help='time segments of the mix (0: distributed.MIX_SEGMENTS)')
-    ap.add_argument('--collective', default='peer', choices=['peer', 'all_reduce', 'reduce'],
-                    help='sum of the per-rank mixes: fused with the render over peer memory (default), or NCCL')
+    ap.add_argument('--collective', default='peer_sharded', choices=['peer_sharded', 'peer', 'all_reduce', 'reduce'],
+                    help='sum of the per-rank mixes: fused with the render over peer memory, result left sharded by time (default) or '
+                         'replicated on every rank (peer), or NCCL after the render')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-single', action='store_true', help='skip the single_source block')
     args = ap.parse_args()

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libbas_b200.so')
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 N_DIRECTIONS = 187
 MAX_TERMS = 16
 AZ_PYFLOAT, AZ_F64, AZ_F32 = 0, 1, 2
@@ -120,7 +120,7 @@ def _load():
         'bas_render_step': ([C.POINTER(StepJob), vp], i),
         'bas_render_routed': ([vp, ll, ll, i, ll, i, i, i, vp, vp, vp, i, vp, ll, ll, vp, ll, vp, i, vp, ll, C.POINTER(Route), vp], i),
         'bas_peer_signal': ([vp, i, i, C.c_uint, vp], i),
-        'bas_peer_reduce': ([vp, i, ll, ll, vp, ll, ll, vp, C.c_uint, vp, i, vp, vp], i),
+        'bas_peer_reduce': ([vp, i, ll, ll, vp, i, ll, ll, vp, C.c_uint, vp, i, vp, vp, vp], i),
         'bas_peer_wait': ([vp, i, C.c_uint, vp], i),
         'bas_render_workspace_bytes': ([], ll),
         'bas_normalise': ([vp, ll, vp, vp], i),

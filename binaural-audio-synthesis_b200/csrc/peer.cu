@@ -6,11 +6,15 @@
 // 16-byte stores to peer-mapped memory: the transfer overlaps the FIR math tile by tile, render_tiled.cuh).
 // What is left for the end of the step are three small kernels on each rank:
 //
-//   bas_peer_signal   "my partial tiles have landed everywhere"   one release-store per peer
+//   bas_peer_signal   "my partial tiles have landed everywhere"   one release-store per peer (or folded into
+//                     bas_peer_reduce: arrive_ptrs_dev)
 //   bas_peer_reduce   wait for every writer's signal; sum the N partial slices in RANK ORDER (deterministic,
-//                     unlike a ring or tree); store the reduced slice into every rank's result buffer;
-//                     the last CTA signals "slice of owner o written" to every peer
-//   bas_peer_wait     wait for every owner's signal: the full mix is now in this rank's result buffer
+//                     unlike a ring or tree); store the reduced slice into the result buffer of n_results ranks
+//                     (every rank: the mix replicated, an all-reduce; only this rank: the mix left sharded by time,
+//                     a reduce-scatter); the last CTA signals "slice of owner o done" to every peer
+//   bas_peer_wait     wait for every owner's signal.  Replicated: at the end of the step - the full mix is now in this
+//                     rank's result buffer.  Sharded: at the START of the next step, before the routed render writes
+//                     into the owners' receive buffers again (flow control, off the critical path)
 //
 // Memory: caller-owned symmetric buffers (torch.distributed._symmetric_memory supplies the peer mappings;
 // this library never allocates).  All waits are bounded by elapsed time (trap instead of hanging the GPU).
@@ -60,10 +64,16 @@ __global__ void bas_peer_wait_kernel(const unsigned* __restrict__ flags, int n, 
 // rank's slice and stores them at result[ear][slice_begin + p] of every rank
 __global__ void __launch_bounds__(256)
 bas_peer_reduce_kernel(const float* __restrict__ recv, int n, long long stride, long long valid, float* const* __restrict__ result_ptrs,
-                       long long result_stride, long long slice_begin, const unsigned* __restrict__ arrived, unsigned epoch,
-                       unsigned* const* __restrict__ done_ptrs, int rank, unsigned* __restrict__ counter) {
+                       int n_results, long long result_stride, long long slice_begin, const unsigned* __restrict__ arrived, unsigned epoch,
+                       unsigned* const* __restrict__ done_ptrs, int rank, unsigned* __restrict__ counter,
+                       unsigned* const* __restrict__ arrive_ptrs) {
     bas_grid_launch_dependents();
     bas_grid_dependency_wait();
+    // folded bas_peer_signal: this rank's render (the previous kernel in the stream) has completed
+    if (arrive_ptrs && blockIdx.x == 0) {
+        __threadfence_system();
+        if ((int)threadIdx.x < n) st_release_sys(arrive_ptrs[threadIdx.x] + rank, epoch);
+    }
     if ((int)threadIdx.x < n) wait_reached(arrived + threadIdx.x, epoch);
     __syncthreads();
     const long long quads = (valid + 3) / 4;                           // stride and slice_begin are multiples of 4
@@ -75,7 +85,7 @@ bas_peer_reduce_kernel(const float* __restrict__ recv, int n, long long stride, 
             const float4 v = *reinterpret_cast<const float4*>(recv + ((long long)w * 2 + ear) * stride + p);
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
-        for (int r = 0; r < n; ++r)
+        for (int r = 0; r < n_results; ++r)
             *reinterpret_cast<float4*>(result_ptrs[r] + (long long)ear * result_stride + slice_begin + p) = acc;
     }
     // the last CTA to finish tells every peer that this owner's slice is complete
@@ -105,16 +115,17 @@ extern "C" int bas_peer_wait(const unsigned* flags_dev, int n, unsigned epoch, v
     return 0;
 }
 
-extern "C" int bas_peer_reduce(const float* recv_dev, int n, long long stride, long long valid, float* const* result_ptrs_dev,
+extern "C" int bas_peer_reduce(const float* recv_dev, int n, long long stride, long long valid, float* const* result_ptrs_dev, int n_results,
                                long long result_stride, long long slice_begin, const unsigned* arrived_dev, unsigned epoch,
-                               unsigned* const* done_ptrs_dev, int rank, unsigned* counter_dev, void* stream) {
+                               unsigned* const* done_ptrs_dev, int rank, unsigned* counter_dev, unsigned* const* arrive_ptrs_dev,
+                               void* stream) {
     BAS_CHECK_ARG(recv_dev && result_ptrs_dev && arrived_dev && done_ptrs_dev && counter_dev, "null pointer");
-    BAS_CHECK_ARG(n >= 1 && n <= 32 && rank >= 0 && rank < n, "ranks");
+    BAS_CHECK_ARG(n >= 1 && n <= 32 && rank >= 0 && rank < n && n_results >= 1 && n_results <= n, "ranks");
     BAS_CHECK_ARG(valid >= 0 && stride >= valid && stride % 4 == 0 && slice_begin % 4 == 0 && result_stride % 4 == 0, "geometry (multiples of 4 floats)");
     const long long quads = 2 * ((valid + 3) / 4);
     long long blocks = bas_ceil_div(quads > 0 ? quads : 1, 256 * 4);
     if (blocks > 148 * 4) blocks = 148 * 4;
     BAS_CUDA(bas_launch(bas_peer_reduce_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, recv_dev, n, stride, valid,
-                        result_ptrs_dev, result_stride, slice_begin, arrived_dev, epoch, done_ptrs_dev, rank, counter_dev));
+                        result_ptrs_dev, n_results, result_stride, slice_begin, arrived_dev, epoch, done_ptrs_dev, rank, counter_dev, arrive_ptrs_dev));
     return 0;
 }

@@ -104,8 +104,12 @@ class PeerMix:
         base = self.buf.data_ptr()
         self._recv, self._arrived, self._done, self._counter = base, base + off_flags, base + off_flags + 256, base + off_flags + 512
         self.result = self.buf[recv_floats:recv_floats + result_floats].view(2, self.result_stride)
+        self._own_result_ptr = torch.tensor([bases[self.rank] + off_result], dtype=torch.int64, device=device)
         self.route = _cabi.Route(table_dev=self._recv_ptrs.data_ptr(), n=n, rank=self.rank, len=self.slice_len, stride=self.stride)
         self.epoch = 0
+        self._pending_wait = False
+        begin = self.rank * self.slice_len
+        self.slice = (begin, max(0, min(n_out, begin + self.slice_len) - begin))      # this rank's stretch of the output
 
     def zero_my_blocks(self):
         """A rank without sources still owes every owner its (all-zero) partial slice."""
@@ -114,17 +118,41 @@ class PeerMix:
             block = self.handle.get_buffer(o, (2 * self.stride,), torch.float32, self.rank * 2 * self.stride)
             block.zero_()
 
-    def finish(self, stream):
-        """After this rank's routed render: signal, reduce this rank's slice, wait for every slice."""
+    def begin(self, stream):
+        """Before a routed render: if the previous step left its result sharded, wait until every owner has finished
+        summing that step's slices - only then may this rank's tiles overwrite the owners' receive buffers."""
+        if self._pending_wait:
+            self._cabi.check(self._cabi.lib.bas_peer_wait(self._done, self.world, self.epoch & 0xffffffff, stream), 'bas_peer_wait')
+            self._pending_wait = False
+
+    def finish(self, stream, replicate=True):
+        """After this rank's routed render: signal, sum this rank's slice in rank order.  replicate=True: the sum is
+        stored into every rank's result buffer and the call waits for all slices - `result` holds the full mix on
+        every rank (an all-reduce).  replicate=False: the sum stays here, `result[:, slice]` is this rank's stretch of
+        the mix (a reduce-scatter; `gather()` assembles it) and the wait moves to the next `begin`."""
         cabi, lib = self._cabi, self._cabi.lib
         self.epoch += 1
         n, e = self.world, self.epoch & 0xffffffff
-        begin = self.rank * self.slice_len
-        valid = max(0, min(self.n_out, begin + self.slice_len) - begin)
-        cabi.check(lib.bas_peer_signal(self._arrived_ptrs.data_ptr(), n, self.rank, e, stream), 'bas_peer_signal')
-        cabi.check(lib.bas_peer_reduce(self._recv, n, self.stride, valid, self._result_ptrs.data_ptr(), self.result_stride, begin,
-                                       self._arrived, e, self._done_ptrs.data_ptr(), self.rank, self._counter, stream), 'bas_peer_reduce')
-        cabi.check(lib.bas_peer_wait(self._done, n, e, stream), 'bas_peer_wait')
+        begin, valid = self.slice
+        table = self._result_ptrs if replicate else self._own_result_ptr
+        cabi.check(lib.bas_peer_reduce(self._recv, n, self.stride, valid, table.data_ptr(), n if replicate else 1, self.result_stride, begin,
+                                       self._arrived, e, self._done_ptrs.data_ptr(), self.rank, self._counter,
+                                       self._arrived_ptrs.data_ptr(), stream), 'bas_peer_reduce')
+        if replicate:
+            cabi.check(lib.bas_peer_wait(self._done, n, e, stream), 'bas_peer_wait')
+        else:
+            self._pending_wait = True
+
+    def gather(self, group=None):
+        """The full (2, n_out) mix on every rank from the sharded result (torch all_gather of the slices)."""
+        import torch.distributed as dist
+        torch = self.torch
+        mine = self.result[:, self.rank * self.slice_len:(self.rank + 1) * self.slice_len]
+        block = torch.zeros((2, self.slice_len), dtype=torch.float32, device=self.result.device)
+        block[:, :mine.shape[1]] = mine
+        blocks = [torch.empty_like(block) for _ in range(self.world)]
+        dist.all_gather(blocks, block, group=group)
+        return torch.cat(blocks, dim=1)[:, :self.n_out]
 
 
 def _default_render(*args, **kwargs):
@@ -237,6 +265,8 @@ def render_mix_by_source(signals, chunksize, subchunksize, elev_azim_functions, 
         job.plan(main.cuda_stream)
 
     def one_pass(gains):
+        if peer is not None:
+            peer.begin(main.cuda_stream)
         for i, (pa, pb) in enumerate(segs):
             if job is not None:
                 if i in uploaded:

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define BAS_ABI_VERSION 3
+#define BAS_ABI_VERSION 4
 
 #define BAS_N_DIRECTIONS 187      /* rows of the measurement grid, sphere.py:127-315 */
 #define BAS_MAX_TERMS 16          /* merged gather terms per ear per trajectory point */
@@ -203,9 +203,14 @@ long long bas_bank2_floats(int U, int K);
  * other tiles are still being computed.  Then, on every rank, in stream order:
  *   bas_peer_signal(arrived_ptrs, n, rank, epoch)   "my tiles have landed": one release-store per peer
  *   bas_peer_reduce(...)                            waits for all n writers, sums their slices in rank order
- *                                                   (deterministic), stores the sum into every rank's result
- *                                                   buffer, and its last CTA signals "slice written" to every peer
- *   bas_peer_wait(done_flags, n, epoch)             all n slices of the full mix are in this rank's result buffer
+ *                                                   (deterministic), stores the sum into the result buffers of
+ *                                                   result_ptrs_dev[0 .. n_results) - every rank (replicated mix) or
+ *                                                   this rank only (mix left sharded by time) - and its last CTA
+ *                                                   signals "slice done" to every peer.  arrive_ptrs_dev != NULL
+ *                                                   folds bas_peer_signal into this launch
+ *   bas_peer_wait(done_flags, n, epoch)             replicated: all n slices are in this rank's result buffer;
+ *                                                   sharded: called before the NEXT routed render, it keeps a fast
+ *                                                   rank from overwriting receive buffers an owner is still summing
  * epoch counts steps (any value that increases by one per step).  Flags, receive and result buffers are the
  * caller's (symmetric allocations; flags and counter zeroed once); every wait is bounded by elapsed time. */
 typedef struct bas_route {
@@ -220,9 +225,10 @@ int bas_render_routed(const float* x_dev, long long x_stride, long long n_valid,
                       float* peaks_dev, int variant, void* workspace_dev, long long workspace_bytes, const bas_route* route,
                       void* stream);
 int bas_peer_signal(unsigned* const* flag_ptrs_dev, int n, int slot, unsigned epoch, void* stream);
-int bas_peer_reduce(const float* recv_dev, int n, long long stride, long long valid, float* const* result_ptrs_dev,
+int bas_peer_reduce(const float* recv_dev, int n, long long stride, long long valid, float* const* result_ptrs_dev, int n_results,
                     long long result_stride, long long slice_begin, const unsigned* arrived_dev, unsigned epoch,
-                    unsigned* const* done_ptrs_dev, int rank, unsigned* counter_dev, void* stream);
+                    unsigned* const* done_ptrs_dev, int rank, unsigned* counter_dev, unsigned* const* arrive_ptrs_dev,
+                    void* stream);
 int bas_peer_wait(const unsigned* flags_dev, int n, unsigned epoch, void* stream);
 
 /* ---- one render step as one call: apply_hrtf.py:429-435 feeding :438-453 and :459-464 ----------
