@@ -370,6 +370,7 @@ def render_geometry(n_samples: int, chunksize: int, subchunksize: int, irs_and_d
 TRAJECTORY_TRIAL_MIN = 24        # fewer boundaries than this: just loop
 TRAJECTORY_CHECKS = 8            # scalar spot checks of the first array evaluation of a callable (first, last, random)
 TRAJECTORY_RECHECKS = 2          # spot checks of later evaluations (later phases of the same call): 12 per 3-phase call
+TRAJECTORY_CHECKS_MANY = 4       # per callable when 16 or more sources are rendered in one call (first, last, two random)
 
 
 def _scalar_point(elev_azim_function, t):
@@ -425,7 +426,7 @@ def evaluate_trajectory(elev_azim_function, times, state=None):
     if declared is None and n >= TRAJECTORY_TRIAL_MIN and state.get('mode') != 'loop':
         first = 'mode' not in state
         rng = state.setdefault('rng', np.random.default_rng(n))
-        res = _try_vectorized(elev_azim_function, times, TRAJECTORY_CHECKS if first else TRAJECTORY_RECHECKS, rng)
+        res = _try_vectorized(elev_azim_function, times, state.get('checks', TRAJECTORY_CHECKS) if first else TRAJECTORY_RECHECKS, rng)
         if res is not None and (first or res[2] == state.get('kind')):
             state['mode'], state['kind'] = 'array', res[2]
             return res
@@ -763,6 +764,8 @@ def _render_pipeline(torch, dev, src, chunksize, subchunksize, elev_azim_functio
         # than the phases' device work for dozens of sources - while the signal upload (the long pole) runs anyway.
         times = np.arange(0, n_in + 1, chunksize, dtype=np.int64)
         for s, fn in enumerate(elev_azim_functions):
+            if n_src >= 16:
+                traj_state[s]['checks'] = TRAJECTORY_CHECKS_MANY      # dozens of callables: the spot checks are the host's long pole
             elev_h[s], azim_h[s], kinds_h[s] = evaluate_trajectory(fn, times, traj_state[s])
         pre = True
         phases = [(pa, pb, 0 if i == 0 else n_pts, n_pts) for i, (pa, pb, _, _) in enumerate(phases)]
@@ -782,6 +785,8 @@ def _render_pipeline(torch, dev, src, chunksize, subchunksize, elev_azim_functio
         uniform = pt1 == pt0 or bool((kinds_h[:, pt0:pt1] == first_kind).all())
         job.az_kind_all = first_kind
         job.az_kind_host = None if uniform else kinds_ptr
+        if PROGRESS and len(phases) > 1 and i:
+            print(' {:.1f}%           '.format(100 * (pa - p0) / max(count, 1)), end='\r')      # apply_hrtf.py:456, once per phase
         _cabi.check(lib.bas_pipeline_phase(C.byref(job), i, len(phases), pt0, pt1, pa, pb), 'bas_pipeline_phase')
     words = small.numpy()[:4 * (2 + n_src)].view(np.int32)
     err, where = _cabi.decode_status(words)

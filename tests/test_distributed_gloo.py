@@ -142,3 +142,16 @@ def test_time_sharded_equals_single_rank(tmp_path, mode):
     assert np.abs(a - want).max() <= 2e-7 * max(1.0, np.abs(want).max())
     if mode == 'time_loud':
         assert abs(np.abs(a).max() - 1.0) < 1e-6
+
+
+def test_mix_segments_cover_the_output_on_the_tile_grid():
+    """distributed.mix_segments: the time segments of a by-source mix (upload / render pipelining) are contiguous,
+    cover [0, n_out) and start on the render tile grid."""
+    import binaural_audio_synthesis_b200 as bas
+    d = bas.distributed
+    for n_out, n_seg in [(2646271, None), (2646271, 1), (9000, 6), (8192, 3), (1, 4), (441599, 8)]:
+        segs = d.mix_segments(n_out, n_seg)
+        assert segs[0][0] == 0 and segs[-1][1] == n_out
+        for (a, b), (c, e) in zip(segs[:-1], segs[1:]):
+            assert b == c and a < b and a % 8192 == 0
+        assert len(segs) <= (n_seg or d.MIX_SEGMENTS)

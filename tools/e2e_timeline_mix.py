@@ -38,3 +38,23 @@ for _ in range(2):
 torch.cuda.synchronize()
 t0 = time.perf_counter(); d.copy_(xt, non_blocking=True); torch.cuda.synchronize(); t1 = time.perf_counter()
 print('plain pinned H2D of %.0f MB: %.2f ms = %.1f GB/s' % (x.nbytes / 1e6, (t1 - t0) * 1e3, x.nbytes / (t1 - t0) / 1e9))
+
+# steady-state per call: pinned + declared vectorised, and pageable + plain lambdas (what bench.py's e2e leg times)
+def loop(xs, fns, reps=8):
+    for _ in range(2):
+        bas.render_sources(xs, 512, 32, fns, bank, mix=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        y = bas.render_sources(xs, 512, 32, fns, bank, mix=True)
+    return (time.perf_counter() - t0) / reps * 1e3
+print('pinned + vectorised: %.2f ms per call' % loop(x, trajs))
+x_page = np.stack([bench.noise_host(n, 100 + s, 0.05 / 8) for s in range(n_src)])
+plain = [bench.lissajous(s) for s in range(n_src)]
+print('pageable + plain lambdas: %.2f ms per call' % loop(x_page, plain))
+import cProfile, pstats, io
+pr = cProfile.Profile(); pr.enable()
+for _ in range(3):
+    bas.render_sources(x_page, 512, 32, plain, bank, mix=True)
+pr.disable()
+s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats('cumulative').print_stats(14); print(s.getvalue()[:3000])
