@@ -116,6 +116,7 @@ def _load():
         'bas_render_fused': ([vp, ll, ll, i, ll, i, i, i, vp, vp, i, vp, ll, ll, vp, ll, i, vp, i, vp, ll, vp], i),
         'bas_render_fused_supported': ([i, i], i),
         'bas_render_fused_shape': ([i], i),
+        'bas_render_fused_fits': ([i, i, i, i, i], i),
         'bas_bank2_floats': ([i, i], ll),
         'bas_render_step': ([C.POINTER(StepJob), vp], i),
         'bas_render_routed': ([vp, ll, ll, i, ll, i, i, i, vp, vp, vp, i, vp, ll, ll, vp, ll, vp, i, vp, ll, C.POINTER(Route), vp], i),

@@ -651,8 +651,8 @@ class DeviceRender:
             np.ascontiguousarray(kinds, dtype=np.uint8).reshape(-1)).to(device)
         if self.kinds_d is not None and self.kinds_d.numel() != n_src * n_pts:
             raise ValueError('az_kind must have one entry per direction')
-        self.fused = bool(_want_fused(dev.taps) and (variant & 0x3f) != _cabi.RENDER_GENERIC and lib.bas_render_fused_supported(chunksize, subchunksize)
-                          and lib.bas_render_fused_shape(variant) and x.data_ptr() % 16 == 0 and (n_src == 1 or x.stride(0) % 4 == 0))
+        self.fused = bool(_want_fused(dev.taps) and lib.bas_render_fused_fits(dev.taps, chunksize, subchunksize, 1 if mix else 0, variant)
+                          and x.data_ptr() % 16 == 0 and (n_src == 1 or x.stride(0) % 4 == 0))
         self.terms = torch.empty(n_src * n_pts * 2 * _cabi.MAX_TERMS * 8, dtype=torch.uint8, device=device)
         self.filt = None if self.fused else torch.empty((n_src * n_pts, lib.bas_filter_row_pitch(dev.taps), 2),
                                                         dtype=torch.float32, device=device)
@@ -737,8 +737,7 @@ def _render_pipeline(torch, dev, src, chunksize, subchunksize, elev_azim_functio
         workspace_dev=workspace.data_ptr(), workspace_bytes=workspace.numel(),
         stream_main=main.cuda_stream, stream_up=up.cuda_stream, stream_down=down.cuda_stream,
         bank_pp2_dev=dev.bank_pp2.data_ptr() if _want_fused(k) else None)
-    fused = bool(_want_fused(k) and (variant & 0x3f) != _cabi.RENDER_GENERIC and lib.bas_render_fused_supported(chunksize, subchunksize)
-                 and lib.bas_render_fused_shape(variant))
+    fused = bool(_want_fused(k) and lib.bas_render_fused_fits(k, chunksize, subchunksize, 1 if mix else 0, variant))
     phases = _phase_plan(p0, p1, n_in, chunksize, 8 * n_rows, n_src)
     cuts = (C.c_longlong * (len(phases) + 1))(*([ph[0] for ph in phases] + [p1]))
     _cabi.check(lib.bas_pipeline_upload(C.byref(job), len(phases), cuts), 'bas_pipeline_upload')

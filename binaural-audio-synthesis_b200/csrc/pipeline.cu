@@ -167,8 +167,7 @@ extern "C" int bas_pipeline_phase(const bas_pipeline_job* j, int phase, int n_ph
     float* out = reinterpret_cast<float*>(arena + l.out);
     float* peaks = reinterpret_cast<float*>(small + 2);
     const long long m = pt_end - pt_begin;
-    const bool fused = j->bank_pp2_dev != nullptr && bas_render_fused_supported(j->C, j->S) && (j->variant & 0x3f) != BAS_RENDER_GENERIC &&
-                       bas_render_fused_shape(j->variant);
+    const bool fused = j->bank_pp2_dev != nullptr && bas_render_fused_fits(j->K, j->C, j->S, j->mix, j->variant);
     mark("phase %lld called", phase, 0, nullptr, true);
 
     if (phase == 0) {                   // status words and peaks: all zero

@@ -281,6 +281,26 @@ extern "C" int bas_render_fused_shape(int variant) {
     return fused_shape_ok(tw, ns ? ns : 2, ctas ? ctas : (tw == 4 ? 2 : 1)) ? 1 : 0;
 }
 
+extern "C" int bas_render_fused_fits(int K, int C, int S, int mix, int variant) {
+    // 1 when bas_render_fused has a tile shape for this geometry (shared memory for the input stages, at least one
+    // filter-row buffer and, when mixing, the running sums) - callers decide up front instead of falling back mid-job
+    if (K < 1 || !bas_render_fused_supported(C, S) || (variant & 0x3f) == BAS_RENDER_GENERIC || !bas_render_fused_shape(variant)) return 0;
+    const int tw_req = (variant >> 8) & 0xff;
+    const int parts_code = (variant >> 28) & 0x7, parts = parts_code ? 1 << (parts_code - 1) : 1;
+    const int idx = (mix ? 1 : 0) + 2 + (S == kBlk / 2 ? 4 : 0);
+    const int pitch = bas_filter_row_pitch(K);
+    for (int tu = 0; tu < 3; ++tu) {
+        int n_shapes = 0;
+        const TiledShape* shapes = tu == 0 ? tiled_shapes_tw4(&n_shapes) : tu == 1 ? tiled_shapes_tw6(&n_shapes) : tiled_shapes_tw8(&n_shapes);
+        for (int i = 0; i < n_shapes; ++i) {
+            if (tw_req && shapes[i].tw != tw_req) continue;
+            if (shapes[i].tw % parts) continue;
+            if (shapes[i].ctas_per_sm[idx](K, C, pitch, parts, true) > 0 || shapes[i].ctas_per_sm[idx](K, C, pitch, parts, false) > 0) return 1;
+        }
+    }
+    return 0;
+}
+
 extern "C" long long bas_bank2_floats(int U, int K) {
     // every phase row twice + padding for the second tap of a gather pass (render_tiled.cuh)
     return U < 1 || K < 1 ? BAS_E_ARG : 2LL * BAS_N_DIRECTIONS * U * 2 * K + 1024;

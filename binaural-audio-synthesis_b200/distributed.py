@@ -284,26 +284,34 @@ def render_mix_by_source(signals, chunksize, subchunksize, elev_azim_functions, 
 
     one_pass(None)
     # ---- status, peaks, and the rare second pass of apply_hrtf.py:462-464 (see render_sources) ---------
-    flag = torch.zeros(1, dtype=torch.int32, device=torch_dev)
-    peaks_host = None
+    # One small MAX all-reduce carries both decisions every rank has to agree on: "some trajectory failed" (then every
+    # rank raises - a rank that raised alone would leave the others waiting in the next collective) and "some source
+    # peaked above 1" (then every rank runs the second pass).
+    flag = torch.zeros(2, dtype=torch.int32, device=torch_dev)
+    peaks_host, failure = None, None
     if job is not None:
         small = job.small.cpu().numpy()
         err, where = decode_status(small)
         if err:
-            ah._raise_plan_error(err, ' (trajectory point %d of local source %d, rank %d)' % (where % job.n_pts, where // job.n_pts, rank))
+            failure = (err, ' (trajectory point %d of local source %d, rank %d)' % (where % job.n_pts, where // job.n_pts, rank))
+            flag[1] = 1
         peaks_host = small[2:].view(np.float32)
         if normalise and (peaks_host > 1).any():
-            flag.fill_(1)
-    if normalise:
-        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
-        if int(flag):
-            gains = None
-            if job is not None:
-                gains = torch.from_numpy((1.0 / np.maximum(peaks_host, 1.0)).astype(np.float32)).to(torch_dev)
-                job.zero_peaks()
-            else:
-                mix.zero_()
-            one_pass(gains)
+            flag[0] = 1
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+    second_pass, failed = (int(v) for v in flag.cpu())
+    if failed:
+        if failure is not None:
+            ah._raise_plan_error(*failure)
+        raise ah.BasError('a trajectory of another rank failed (see that rank\'s exception)')
+    if second_pass:
+        gains = None
+        if job is not None:
+            gains = torch.from_numpy((1.0 / np.maximum(peaks_host, 1.0)).astype(np.float32)).to(torch_dev)
+            job.zero_peaks()
+        else:
+            mix.zero_()
+        one_pass(gains)
     result = peer.result[:, :n_out].clone() if peer is not None else mix[:, :n_out]
     if dst is None or rank == dst:
         return result

@@ -192,6 +192,7 @@ int bas_render_fused(const float* x_dev, long long x_stride, long long n_valid, 
                      int mix, float* peaks_dev, int variant, void* workspace_dev, long long workspace_bytes, void* stream);
 int bas_render_fused_supported(int C, int S);
 int bas_render_fused_shape(int variant);      /* 1: the tile shape `variant` requests is compiled for the fused kernel */
+int bas_render_fused_fits(int K, int C, int S, int mix, int variant);   /* 1: some fused tile shape fits this geometry (needs a device) */
 long long bas_bank2_floats(int U, int K);
 
 /* ---- by-source sharding over several GPUs: the per-rank mixes summed over peer memory ----

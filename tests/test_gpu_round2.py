@@ -237,3 +237,21 @@ def test_cli_scene_mixes_several_sources(bas, oracle, golden_bank, tmp_path):
     want = (oracle.make_signal_move_2d(xa, 256, 32, traj['circle_horizontal'], golden_bank).astype(np.float64) +
             oracle.make_signal_move_2d(xb, 256, 32, lambda t: traj['passing'](t - lead), golden_bank))
     close(got.astype(np.float64), want)
+
+
+@pytest.mark.parametrize('chunk,sub', [(32, 32), (64, 16), (96, 32), (2048, 64), (4096, 4096)])
+def test_chunk_sizes_the_fused_kernel_cannot_stage_fall_back_up_front(bas, oracle, synth_bank, chunk, sub):
+    """Tiny chunks mean hundreds of filter rows per tile: no fused shape fits shared memory.  The decision is taken
+    before the job starts (bas_render_fused_fits), for host arrays (pipeline.cu) and device tensors alike."""
+    import torch
+    bas.apply_hrtf.PROGRESS = False
+    rng = np.random.default_rng(chunk + sub)
+    x = (0.05 * rng.standard_normal(5000)).astype(np.float32)
+    want = oracle.make_signal_move_2d(x, chunk, sub, _traj(3), synth_bank)
+    close(bas.make_signal_move_2d(x, chunk, sub, _traj(3), synth_bank), want)
+    n_in = -(-x.size // chunk) * chunk
+    xd = torch.zeros((2, n_in), dtype=torch.float32, device='cuda')
+    xd[:, :x.size] = torch.from_numpy(x).cuda()
+    mix = bas.render_sources(xd, chunk, sub, [_traj(3), _traj(3)], synth_bank, mix=True, normalise=False, return_device=True).cpu().numpy()
+    want_n_in = oracle.make_signal_move_2d(np.concatenate([x, np.zeros(n_in - x.size, dtype=np.float32)]), chunk, sub, _traj(3), synth_bank)
+    close(mix.T, 2.0 * want_n_in)
