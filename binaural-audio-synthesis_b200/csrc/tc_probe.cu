@@ -218,13 +218,227 @@ bas_probe_tc_kernel(const float* __restrict__ x, long long n_in, const float2* _
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// mode 3: the same contraction PIPELINED and complete (no atomics): one CTA per SM owns a contiguous range of 512-sample
+// output chunks and walks over the boundaries that feed it.  Nine warps, three roles, double-buffered operands and
+// accumulators:   warps 5-8 stage the operands of boundary k+1 | warp 4 issues the 60 MMAs of boundary k |
+//                 warps 0-3 load the accumulators of boundary k-1 from TMEM, overlap-add them in registers, add them to a
+//                 2048-sample output ring in shared memory and flush the chunk that is now complete to global memory.
+// ------------------------------------------------------------------------------------------------------------
+struct PipeSmem {
+    float4 w[2][2][kWSlots];                  // [buffer][hi / lo]
+    float4 b[2][2][256];
+    float g[2][kGLen];                        // stagers' scratch: padded taps, hi / lo
+    float ring[2][2048];                      // output ring per ear: samples [512 (i-1), 512 (i-1) + 2048) of the boundary in flight
+    unsigned long long op_full[2], op_empty[2], tm_full[2], tm_empty[2];
+    unsigned tmem_base;
+};
+
+__device__ __forceinline__ void bar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok = 0;
+    unsigned long long t0 = 0;
+    for (unsigned spins = 0; !ok; ++spins) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(s32(bar)), "r"(parity) : "memory");
+        if (!ok && (spins & 1023u) == 1023u) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+            if (!t0) t0 = now;
+            else if (now - t0 > 5000000000ull) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void bar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(288, 1)
+bas_probe_tc_pipe_kernel(const float* __restrict__ x, long long n_in, const float2* __restrict__ filt, int pitch, int K, int C,
+                         float* __restrict__ out, long long out_stride, long long n_out) {
+    extern __shared__ __align__(128) unsigned char raw[];
+    PipeSmem& sm = *reinterpret_cast<PipeSmem*>(raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_chunks = (int)(n_in / C);
+    const int spc = C / 32;
+    const int out_chunks = (int)((n_out + C - 1) / C);
+    // this CTA's output chunks [c0, c1) and the boundaries that feed them
+    const int c0 = (int)((long long)blockIdx.x * out_chunks / gridDim.x), c1 = (int)((long long)(blockIdx.x + 1) * out_chunks / gridDim.x);
+    const int i_first = c0 - 1 < 0 ? 0 : c0 - 1, i_last = c1 > n_chunks ? n_chunks : c1;
+    const int nb = c1 > c0 ? i_last - i_first + 1 : 0;
+
+    if (tid == 0) {
+        for (int b = 0; b < 2; ++b) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(s32(&sm.op_full[b])) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&sm.op_empty[b])) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&sm.tm_full[b])) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(s32(&sm.tm_empty[b])) : "memory");
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int k = tid; k < 2 * 2048; k += 288) (&sm.ring[0][0])[k] = 0.f;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(s32(&sm.tmem_base)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem = sm.tmem_base;
+    const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+
+    if (warp >= 5) {
+        // ================================ stagers ================================
+        const int st = tid - 160;
+        for (int k = 0; k < nb; ++k) {
+            const int i = i_first + k, b = k & 1, u = k >> 1;
+            const float2* row = filt + (long long)i * pitch;
+            asm volatile("bar.sync 2, 128;" ::: "memory");                 // the previous boundary's expansion has read g
+            for (int e = st; e < kGLen; e += 128) {
+                float v = 0.f;
+                const int tl = e - 31, tr = e - 31 - kRowsPerEar;
+                if (tl >= 0 && tl < K) v = row[tl].x;
+                else if (tr >= 0 && tr < K) v = row[tr].y;
+                const float hi = tf32_hi(v);
+                sm.g[0][e] = hi;
+                sm.g[1][e] = v - hi;
+            }
+            if (u >= 1) bar_wait(&sm.op_empty[b], (unsigned)((u - 1) & 1));   // the MMAs that read this buffer have completed
+            for (int e = st; e < 256; e += 128) {
+                const int kchunk = e >> 5, n = e & 31;
+                const int chunk = i - 1 + (n >= spc ? 1 : 0);
+                const int q = n >= spc ? n - spc : n;
+                const float alpha = (float)(q * 32) / (float)C;
+                const float s = n >= spc ? 1.f - alpha : alpha;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (chunk >= 0 && chunk < n_chunks) v = *reinterpret_cast<const float4*>(x + (long long)chunk * C + 32 * q + 28 - 4 * kchunk);
+                // reversed within the row: element e' of the unit is sample 31 - (4 kchunk + e')
+                const float r0 = s * v.w, r1 = s * v.z, r2 = s * v.y, r3 = s * v.x;
+                const float h0 = tf32_hi(r0), h1 = tf32_hi(r1), h2 = tf32_hi(r2), h3 = tf32_hi(r3);
+                sm.b[b][0][e] = make_float4(h0, h1, h2, h3);
+                sm.b[b][1][e] = make_float4(r0 - h0, r1 - h1, r2 - h2, r3 - h3);
+            }
+            asm volatile("bar.sync 2, 128;" ::: "memory");                 // g complete
+            for (int j = st; j < kWSlots; j += 128) {
+                sm.w[b][0][j] = make_float4(sm.g[0][j], sm.g[0][j + 1], sm.g[0][j + 2], sm.g[0][j + 3]);
+                sm.w[b][1][j] = make_float4(sm.g[1][j], sm.g[1][j + 1], sm.g[1][j + 2], sm.g[1][j + 3]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            bar_arrive(&sm.op_full[b]);
+        }
+    } else if (warp == 4) {
+        // ================================ MMA issuer ================================
+        for (int k = 0; k < nb; ++k) {
+            const int b = k & 1, u = k >> 1;
+            bar_wait(&sm.op_full[b], (unsigned)(u & 1));
+            if (u >= 1) bar_wait(&sm.tm_empty[b], (unsigned)((u - 1) & 1));   // the epilogue has drained this accumulator buffer
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const unsigned wa[2] = {s32(&sm.w[b][0][0]), s32(&sm.w[b][1][0])};
+                const unsigned ba[2] = {s32(&sm.b[b][0][0]), s32(&sm.b[b][1][0])};
+#pragma unroll 1
+                for (int t = 0; t < kMTiles; ++t) {
+                    unsigned acc = 0;
+#pragma unroll
+                    for (int split = 0; split < 3; ++split) {
+                        const int sa = split == 2 ? 1 : 0, sb = split == 1 ? 1 : 0;
+#pragma unroll
+                        for (int s = 0; s < 4; ++s) {
+                            mma_tf32(tmem + 256u * b + 32u * t, smem_desc(wa[sa] + 16u * (128u * t + 8u * s), 64u, 128u),
+                                     smem_desc(ba[sb] + 16u * (64u * s), 512u, 128u), idesc, acc);
+                            acc = 1;
+                        }
+                    }
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&sm.op_empty[b])) : "memory");
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&sm.tm_full[b])) : "memory");
+            }
+            __syncwarp();
+        }
+    } else {
+        // ================================ epilogue ================================
+        for (int k = 0; k < nb; ++k) {
+            const int i = i_first + k, b = k & 1, u = k >> 1;
+            bar_wait(&sm.tm_full[b], (unsigned)(u & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            float olaL[40], olaR[40];
+#pragma unroll
+            for (int e = 0; e < 40; ++e) { olaL[e] = 0.f; olaR[e] = 0.f; }
+#pragma unroll
+            for (int t = 0; t < kMTiles; ++t) {
+                float v[32];
+                tmem_ld32(tmem + ((unsigned)(warp * 32) << 16) + 256u * b + 32u * t, v);
+                // rows 128 t + 32 warp + lane: ear L below row 320 (block n + 4 t + warp), ear R from row 320 (block n + 4 t - 10 + warp)
+                if (t < 2 || (t == 2 && warp < 2)) {
+#pragma unroll
+                    for (int n = 0; n < 32; ++n) olaL[n + 4 * (t < 2 ? t : 2)] += v[n];
+                } else {
+#pragma unroll
+                    for (int n = 0; n < 32; ++n) olaR[n + 4 * (t - 2)] += v[n];
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            bar_arrive(&sm.tm_empty[b]);                                   // the accumulators are in registers: the buffer may be overwritten
+            const long long base = (long long)(i - 1) * C;                 // first output sample of this boundary (may be -512)
+            const unsigned rb = (unsigned)(((i - 1) & 3) * C);             // its place in the 2048-sample ring
+#pragma unroll
+            for (int e = 0; e < 40; ++e) {
+                atomicAdd(&sm.ring[0][(rb + 32u * (unsigned)(e + warp) + lane) & 2047u], olaL[e]);
+                atomicAdd(&sm.ring[1][(rb + 32u * (unsigned)(e + warp - 2 + 2) + lane - 64u) & 2047u], olaR[e]);
+            }
+            asm volatile("bar.sync 3, 128;" ::: "memory");
+            // chunk i - 1 is complete: no later boundary adds to it
+            const int chunk = i - 1;
+            {
+                const int ear = tid >> 6, o = (tid & 63) * 8;               // 128 threads x 8 samples = 2 ears x 512
+                float* r = &sm.ring[ear][(rb + o) & 2047u];
+                const float4 a = *reinterpret_cast<float4*>(r), c = *reinterpret_cast<float4*>(r + 4);
+                *reinterpret_cast<float4*>(r) = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(r + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (chunk >= c0 && chunk < c1) {
+                    const long long p = base + o;
+                    float* dst = out + (long long)ear * out_stride + p;
+                    if (p + 8 <= n_out) {
+                        *reinterpret_cast<float4*>(dst) = a;
+                        *reinterpret_cast<float4*>(dst + 4) = c;
+                    } else {
+                        const float vals[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+                        for (int e = 0; e < 8; ++e) if (p + e < n_out) dst[e] = vals[e];
+                    }
+                }
+            }
+            asm volatile("bar.sync 3, 128;" ::: "memory");
+        }
+        // the last CTA also owns the K - 1 sample tail after the last boundary: chunk i_last is complete, nothing follows
+        for (int chunk = i_last; chunk < c1 && nb > 0; ++chunk) {
+            const int ear = tid >> 6, o = (tid & 63) * 8;
+            const float* r = &sm.ring[ear][(unsigned)((chunk & 3) * C + o) & 2047u];
+            const long long p = (long long)chunk * C + o;
+            float* dst = out + (long long)ear * out_stride + p;
+            for (int e = 0; e < 8; ++e) if (p + e < n_out) dst[e] = r[e];
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
 }  // namespace
 
 extern "C" int bas_probe_tc_render(const float* x_dev, long long n_in, const float* filt_dev, int K, int C, float* out_dev,
                                    long long out_stride, long long n_out, int mode, int blocks, float* sink_dev, void* stream) {
     BAS_CHECK_ARG(x_dev && filt_dev && out_dev, "null pointer");
     BAS_CHECK_ARG(K >= 1 && K + 31 <= kRowsPerEar - 31 && C == 512 && n_in % C == 0, "probe geometry: K <= 258, chunksize 512");
-    BAS_CHECK_ARG(mode >= 0 && mode <= 2 && blocks >= 1, "mode / blocks");
+    BAS_CHECK_ARG(mode >= 0 && mode <= 3 && blocks >= 1, "mode / blocks");
+    if (mode == 3) {
+        BAS_CHECK_ARG(out_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(out_dev) & 15) == 0 && (reinterpret_cast<uintptr_t>(x_dev) & 15) == 0, "alignment");
+        const size_t smem3 = sizeof(PipeSmem) > 120 * 1024 ? sizeof(PipeSmem) : 120 * 1024;   // one CTA per SM (all 512 TMEM columns)
+        BAS_CUDA(cudaFuncSetAttribute(bas_probe_tc_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+        bas_probe_tc_pipe_kernel<<<blocks, 288, smem3, (cudaStream_t)stream>>>(x_dev, n_in, reinterpret_cast<const float2*>(filt_dev),
+                                                                               (K + 31) / 32 * 32 + 2, K, C, out_dev, out_stride, n_out);
+        BAS_LAUNCH_CHECK();
+        return 0;
+    }
     const int pitch = (K + 31) / 32 * 32 + 2;
     const size_t smem = sizeof(TcSmem) > 120 * 1024 ? sizeof(TcSmem) : 120 * 1024;      // one CTA per SM: TMEM is allocated per CTA
     BAS_CUDA(cudaFuncSetAttribute(bas_probe_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

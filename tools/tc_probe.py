@@ -82,6 +82,17 @@ for name, arr in (('tc', got), ('simt', ref32)):
     a = arr[:, :win - 1]
     res['%s_vs_oracle_rel_l2' % name] = float(np.linalg.norm(a - wantT) / np.linalg.norm(wantT))
     res['%s_vs_oracle_max_abs_over_peak' % name] = float(np.abs(a - wantT).max() / np.abs(wantT).max())
+# mode 3: the pipelined, complete kernel (no atomics)
+out3 = torch.full((2, stride), float('nan'), dtype=torch.float32, device=dev)
+rc = probe.bas_probe_tc_render(x.data_ptr(), n_in, job.filt.data_ptr(), k, C, out3.data_ptr(), stride, n_out, 3, 148, sink.data_ptr(), st)
+assert rc == 0, rc
+torch.cuda.synchronize()
+got3 = out3[:, :n_out].double().cpu().numpy()
+res['pipelined_all_outputs_written'] = bool(np.isfinite(got3).all())
+res['pipelined_vs_simt_rel_l2'] = float(np.linalg.norm(np.nan_to_num(got3) - ref32) / np.linalg.norm(ref32))
+a3 = np.nan_to_num(got3[:, :win - 1])
+res['pipelined_vs_oracle_rel_l2'] = float(np.linalg.norm(a3 - wantT) / np.linalg.norm(wantT))
+res['pipelined_vs_oracle_max_abs_over_peak'] = float(np.abs(a3 - wantT).max() / np.abs(wantT).max())
 res['tolerance'] = 1e-5
 res['accuracy_ok'] = bool(res['tc_vs_oracle_rel_l2'] <= 1e-5 and res['tc_vs_oracle_max_abs_over_peak'] <= 1e-5)
 
@@ -89,6 +100,10 @@ useful = 2.0 * k * n_in
 ms_simt = timed(lambda: job.render(st, 0, n_out, simt.data_ptr(), stride))
 ms = {m: timed(lambda m=m: tc(m)) for m in (2, 1)}
 ms0 = timed(lambda: tc(0), reps=3)
+ms3 = timed(lambda: probe.bas_probe_tc_render(x.data_ptr(), n_in, job.filt.data_ptr(), k, C, out3.data_ptr(), stride, n_out, 3, 148, sink.data_ptr(), st))
+res['tc_pipelined_complete_ms'] = ms3
+res['tc_pipelined_tfma_s_equivalent'] = useful / (ms3 * 1e-3) / 1e12
+res['tc_pipelined_speedup_vs_simt_one_source'] = ms_simt / ms3
 res['simt_render_ms'] = ms_simt
 res['simt_tfma_s'] = useful / (ms_simt * 1e-3) / 1e12
 res['tc_mma_only_ms'] = ms[2]
