@@ -102,8 +102,11 @@ bas_probe_tc_kernel(const float* __restrict__ x, long long n_in, const float2* _
     float keep = 0.f;
 
     for (int i = blockIdx.x; i <= n_chunks; i += gridDim.x) {
+        // mode 4: operands staged once, then only the 60 MMAs per boundary - the tensor-core rate of this shape on its own
+        const bool stage = mode != 4 || i == (int)blockIdx.x;
         // ---- g: the zero-padded taps of boundary filter i, ear L at u = 31 .. 31 + K - 1, ear R 320 rows later
         const float2* row = filt + (long long)i * pitch;
+        if (stage) {
         for (int u = tid; u < kGLen; u += 128) {
             float v = 0.f;
             const int tl = u - 31, tr = u - 31 - kRowsPerEar;
@@ -137,6 +140,7 @@ bas_probe_tc_kernel(const float* __restrict__ x, long long n_in, const float2* _
             sm.w[1][j] = make_float4(sm.g[1][j], sm.g[1][j + 1], sm.g[1][j + 2], sm.g[1][j + 3]);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // generic-proxy writes -> visible to the tensor core
+        }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -180,7 +184,7 @@ bas_probe_tc_kernel(const float* __restrict__ x, long long n_in, const float2* _
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
         // ---- epilogue: row r = 128 t + 32 warp + lane of every M-tile, 32 columns each
-        if (mode != 2) {
+        if (mode != 2 && mode != 4) {
             float ola[16 + 32];                                              // mode 1: overlap-add in registers, block index n + 4 t (+ warp)
 #pragma unroll
             for (int k = 0; k < 48; ++k) ola[k] = 0.f;
@@ -429,7 +433,7 @@ extern "C" int bas_probe_tc_render(const float* x_dev, long long n_in, const flo
                                    long long out_stride, long long n_out, int mode, int blocks, float* sink_dev, void* stream) {
     BAS_CHECK_ARG(x_dev && filt_dev && out_dev, "null pointer");
     BAS_CHECK_ARG(K >= 1 && K + 31 <= kRowsPerEar - 31 && C == 512 && n_in % C == 0, "probe geometry: K <= 258, chunksize 512");
-    BAS_CHECK_ARG(mode >= 0 && mode <= 3 && blocks >= 1, "mode / blocks");
+    BAS_CHECK_ARG(mode >= 0 && mode <= 4 && blocks >= 1, "mode / blocks");
     if (mode == 3) {
         BAS_CHECK_ARG(out_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(out_dev) & 15) == 0 && (reinterpret_cast<uintptr_t>(x_dev) & 15) == 0, "alignment");
         const size_t smem3 = sizeof(PipeSmem) > 120 * 1024 ? sizeof(PipeSmem) : 120 * 1024;   // one CTA per SM (all 512 TMEM columns)

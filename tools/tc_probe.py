@@ -100,6 +100,10 @@ useful = 2.0 * k * n_in
 ms_simt = timed(lambda: job.render(st, 0, n_out, simt.data_ptr(), stride))
 ms = {m: timed(lambda m=m: tc(m)) for m in (2, 1)}
 ms0 = timed(lambda: tc(0), reps=3)
+ms4 = timed(lambda: tc(4))
+res['tc_mma_only_operands_staged_once_ms'] = ms4
+res['tc_cycles_per_mma_m128_n32_k8_tf32'] = ms4 * 1e-3 * 1.965e9 / (60.0 * -(-n_pts // 148))
+res['tc_tensor_tflops_mma_rate'] = 2.0 * 60 * 128 * 32 * 8 * n_pts / (ms4 * 1e-3) / 1e12
 ms3 = timed(lambda: probe.bas_probe_tc_render(x.data_ptr(), n_in, job.filt.data_ptr(), k, C, out3.data_ptr(), stride, n_out, 3, 148, sink.data_ptr(), st))
 res['tc_pipelined_complete_ms'] = ms3
 res['tc_pipelined_tfma_s_equivalent'] = useful / (ms3 * 1e-3) / 1e12
