@@ -15,7 +15,8 @@ for libname in ('libbas_b200.so', 'libbas_probe.so'):
         m = re.search(r'Function : (\S+)', line)
         if m:
             name = subprocess.run(['c++filt', m.group(1)], capture_output=True, text=True).stdout.strip()
-            name = re.sub(r'\(.*', '', name).replace('void ', '').replace('bas_render_detail::', '').replace('(anonymous namespace)::', '')
+            name = name.replace('(anonymous namespace)::', '').replace('void ', '').replace('bas_render_detail::', '')
+            name = re.sub(r'\(.*', '', name)
             cur = kernels.setdefault(name, collections.Counter())
             continue
         m = re.match(r'\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)((?:\.[A-Z0-9_]+)*)', line)
