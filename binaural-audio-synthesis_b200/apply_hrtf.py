@@ -757,17 +757,17 @@ def _render_pipeline(torch, dev, src, chunksize, subchunksize, elev_azim_functio
         raise ValueError('need one trajectory per source')
     kinds_ptr = staged.data_ptr() + n_dirs * 16
     traj_state = [{} for _ in range(n_src)]
-    if pre is None and n_src >= 4 and len(phases) > 1:
-        # Many sources: one array evaluation per trajectory for the whole signal, before the first phase, and ONE plan
-        # launch for all boundaries.  Per-phase evaluation (below) costs a Python round trip per source and phase - more
-        # than the phases' device work for dozens of sources - while the signal upload (the long pole) runs anyway.
-        times = np.arange(0, n_in + 1, chunksize, dtype=np.int64)
-        for s, fn in enumerate(elev_azim_functions):
-            if n_src >= 16:
-                traj_state[s]['checks'] = TRAJECTORY_CHECKS_MANY      # dozens of callables: the spot checks are the host's long pole
-            elev_h[s], azim_h[s], kinds_h[s] = evaluate_trajectory(fn, times, traj_state[s])
-        pre = True
-        phases = [(pa, pb, 0 if i == 0 else n_pts, n_pts) for i, (pa, pb, _, _) in enumerate(phases)]
+    if pre is None and n_src >= 4 and len(phases) > 2:
+        # Many sources: a Python round trip per source and phase costs more than the phases' device work, and the
+        # signal upload (the long pole) runs anyway.  Two evaluations per trajectory instead: the stretch the first
+        # phase needs - so that rendering starts early - and all the rest while that phase uploads and renders;
+        # one plan launch each.
+        pt_a = phases[0][3]
+        phases = [(pa, pb, 0, pt_a) if i == 0 else (pa, pb, pt_a, n_pts) if i == 1 else (pa, pb, n_pts, n_pts)
+                  for i, (pa, pb, _, _) in enumerate(phases)]
+        if n_src >= 16:
+            for st in traj_state:
+                st['checks'] = TRAJECTORY_CHECKS_MANY          # dozens of callables: the spot checks are the host's long pole
     elif pre is not None:
         phases = [(pa, pb, 0 if i == 0 else n_pts, n_pts) for i, (pa, pb, _, _) in enumerate(phases)]
     for i, (pa, pb, pt0, pt1) in enumerate(phases):
