@@ -21,7 +21,7 @@ RENDER_AUTO, RENDER_GENERIC, RENDER_TILED = 0, 1, 2
 RENDER_SPLIT, RENDER_NO_SPLIT = 0x40, 0x80
 MIX_ACCUMULATE = 2
 IR_UPSAMPLED, IR_PLANAR, IR_ROWS = 0, 1, 2
-TILED_SHAPES = ((2, 1, 6), (4, 2, 2), (4, 1, 2), (4, 1, 3), (6, 1, 2), (6, 2, 1), (8, 2, 1), (8, 1, 1))   # (warps per CTA, stages, CTAs per SM)
+TILED_SHAPES = ((4, 2, 2), (4, 1, 2), (4, 1, 3), (6, 1, 2), (6, 2, 1), (8, 2, 1), (8, 1, 1))   # (warps per CTA, stages, CTAs per SM)
 
 
 def render_variant(tw=0, ns=0, ctas=0, parts=0, split=None, base=RENDER_TILED):

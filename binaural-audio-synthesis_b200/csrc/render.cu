@@ -189,9 +189,9 @@ static int render_common(const float* x_dev, long long x_stride, long long n_val
         const TiledShape* best = nullptr;
         int best_parts = 0;
         double best_cost = 0.0;
-        for (int tu = 0; tu < 4; ++tu) {
+        for (int tu = 0; tu < 3; ++tu) {
             int n_shapes = 0;
-            const TiledShape* shapes = tu == 0 ? tiled_shapes_tw4(&n_shapes) : tu == 1 ? tiled_shapes_tw6(&n_shapes) : tu == 2 ? tiled_shapes_tw8(&n_shapes) : tiled_shapes_tw2(&n_shapes);
+            const TiledShape* shapes = tu == 0 ? tiled_shapes_tw4(&n_shapes) : tu == 1 ? tiled_shapes_tw6(&n_shapes) : tiled_shapes_tw8(&n_shapes);
             for (int i = 0; i < n_shapes; ++i) {
                 const TiledShape& sh = shapes[i];
                 if ((tw_req && sh.tw != tw_req) || (ns_req && sh.ns != ns_req) || (cta_req && sh.minb != cta_req)) continue;
@@ -212,15 +212,13 @@ static int render_common(const float* x_dev, long long x_stride, long long n_val
                     if (!(can_split && waves > 1.0)) {
                         // whole tiles, dealt round-robin; the last wave only occupies part of every SM and
                         // its CTAs then run with fewer neighbours on the FMA pipe
-                        // the tail wave puts ceil(rest * ctas) CTAs on the fullest SM; below a full SM they run a little faster each
                         const double full = (double)(long long)waves, rest = waves - full;
-                        const double tail_ctas = rest > 0.0 ? (double)(long long)(rest * ctas + 0.999999) : 0.0;
-                        waves = full + (tail_ctas >= ctas ? 1.0 : tail_ctas > 0.0 ? tail_ctas / ctas + (ctas <= 3 ? (tail_ctas == 1.0 ? 0.25 : 0.15) : 0.08) : 0.0);
+                        waves = full + (rest > 0.0 ? (rest * ctas <= 1.0 ? 1.0 / ctas + 0.25 : rest * ctas <= 2.0 ? 2.0 / ctas + 0.15 : 1.0) : 0.0);
                     }
                     const int wps = (ctas * sh.tw + 3) / 4;
                     double cost = waves * blocks_per_tile * wps;
                     cost *= 1.0 + 0.25 * (parts - 1) + (sh.ns == 1 && ctas == 1 ? 0.02 : 0.0) + (wps < 2 ? 0.3 : 0.0) +
-                            (prm.mix ? (sh.tw == 8 ? -0.05 : sh.minb == 3 ? 0.03 : 0.0) : (sh.tw <= 4 ? 0.0 : 0.05));
+                            (prm.mix ? (sh.tw == 8 ? -0.05 : sh.minb == 3 ? 0.03 : 0.0) : (sh.tw == 4 ? 0.0 : 0.05));
                     if (!best || cost < best_cost) { best = &sh; best_parts = parts; best_cost = cost; }
                 }
             }
@@ -291,9 +289,9 @@ extern "C" int bas_render_fused_fits(int K, int C, int S, int mix, int variant) 
     const int parts_code = (variant >> 28) & 0x7, parts = parts_code ? 1 << (parts_code - 1) : 1;
     const int idx = (mix ? 1 : 0) + 2 + (S == kBlk / 2 ? 4 : 0);
     const int pitch = bas_filter_row_pitch(K);
-    for (int tu = 0; tu < 4; ++tu) {
+    for (int tu = 0; tu < 3; ++tu) {
         int n_shapes = 0;
-        const TiledShape* shapes = tu == 0 ? tiled_shapes_tw4(&n_shapes) : tu == 1 ? tiled_shapes_tw6(&n_shapes) : tu == 2 ? tiled_shapes_tw8(&n_shapes) : tiled_shapes_tw2(&n_shapes);
+        const TiledShape* shapes = tu == 0 ? tiled_shapes_tw4(&n_shapes) : tu == 1 ? tiled_shapes_tw6(&n_shapes) : tiled_shapes_tw8(&n_shapes);
         for (int i = 0; i < n_shapes; ++i) {
             if (tw_req && shapes[i].tw != tw_req) continue;
             if (shapes[i].tw % parts) continue;

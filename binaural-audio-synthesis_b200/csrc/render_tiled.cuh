@@ -885,7 +885,6 @@ struct TiledShape {
 
 // defined in render_tw4.cu / render_tw6.cu / render_tw8.cu (one translation unit per tile width, so
 // they compile in parallel)
-const TiledShape* tiled_shapes_tw2(int* count);
 const TiledShape* tiled_shapes_tw4(int* count);
 const TiledShape* tiled_shapes_tw6(int* count);
 const TiledShape* tiled_shapes_tw8(int* count);

@@ -26,7 +26,7 @@ def timed(fn, reps=10):
 res = {}
 for fused in (True, False):
     ah.FUSED = fused
-    for (tw, ns, ctas) in ((4, 2, 2), (8, 2, 1)) if fused else ((2, 1, 6), (4, 1, 3), (4, 2, 2), (8, 2, 1)):
+    for (tw, ns, ctas) in ((4, 2, 2), (8, 2, 1)) if fused else ((4, 1, 3), (4, 2, 2), (8, 2, 1)):
         for parts in (1, 2):
             for split in (False, True):
                 v = cabi.render_variant(tw, ns, ctas, parts, split=split)
