@@ -76,7 +76,7 @@ class Route(C.Structure):
 class StepJob(C.Structure):
     """bas_step_job (include/bas_b200.h)."""
     _fields_ = [('n_src', C.c_int), ('C', C.c_int), ('S', C.c_int), ('K', C.c_int), ('U', C.c_int), ('mix', C.c_int),
-                ('variant', C.c_int), ('az_kind_all', C.c_int), ('flags', C.c_int), ('n_pre', C.c_int),
+                ('variant', C.c_int), ('az_kind_all', C.c_int), ('flags', C.c_int), ('reserved', C.c_int),
                 ('n_valid', C.c_longlong), ('n_in', C.c_longlong), ('x_stride', C.c_longlong),
                 ('p_begin', C.c_longlong), ('p_count', C.c_longlong), ('out_stride', C.c_longlong),
                 ('x_dev', C.c_void_p), ('elev_dev', C.c_void_p), ('azim_dev', C.c_void_p), ('az_kind_dev', C.c_void_p),

@@ -631,13 +631,6 @@ def _want_fused(taps: int) -> bool:
     return bool(FUSED) if FUSED in (True, False) else taps <= FUSED_MAX_TAPS
 
 
-# Mixing, fused: the producer warps sustain the gathers of about 5 sources in 6 at the rate the FIR blocks consume
-# them (66.9 against 56.4 us per source).  One source in FUSED_PRE_EVERY therefore still gets its rows from a
-# bas_ir_synth launch ahead of the render (23 us each, device-wide) and the render kernel merely copies them:
-# the producers keep pace and the step is bound by the FMA pipe again.  0 switches this off.
-FUSED_PRE_EVERY = 6
-
-
 
 class DeviceRender:
     """Sources resident in HBM, planned once, rendered range by range: the device half of
@@ -661,15 +654,14 @@ class DeviceRender:
         self.fused = bool(_want_fused(dev.taps) and lib.bas_render_fused_fits(dev.taps, chunksize, subchunksize, 1 if mix else 0, variant)
                           and x.data_ptr() % 16 == 0 and (n_src == 1 or x.stride(0) % 4 == 0))
         self.terms = torch.empty(n_src * n_pts * 2 * _cabi.MAX_TERMS * 8, dtype=torch.uint8, device=device)
-        self.n_pre = -(-n_src // FUSED_PRE_EVERY) if (self.fused and mix and FUSED_PRE_EVERY and n_src >= FUSED_PRE_EVERY) else 0
-        n_filt = n_src if not self.fused else self.n_pre
-        self.filt = torch.empty((n_filt * n_pts, lib.bas_filter_row_pitch(dev.taps), 2), dtype=torch.float32, device=device) if n_filt else None
+        self.filt = None if self.fused else torch.empty((n_src * n_pts, lib.bas_filter_row_pitch(dev.taps), 2),
+                                                        dtype=torch.float32, device=device)
         self.small = torch.empty(2 + n_src, dtype=torch.int32, device=device)      # zeroed by plan()
         self.peaks = self.small[2:].view(torch.float32)
         self.workspace = _cabi.render_workspace(torch, device)
         self.job = _cabi.StepJob(
             n_src=n_src, C=chunksize, S=subchunksize, K=dev.taps, U=dev.upsampling, mix=1 if mix else 0, variant=variant,
-            az_kind_all=_cabi.AZ_F64 if self.kinds_d is not None else int(kinds), flags=0, n_pre=self.n_pre,
+            az_kind_all=_cabi.AZ_F64 if self.kinds_d is not None else int(kinds), flags=0,
             n_valid=n_in, n_in=n_in, x_stride=x.stride(0) if n_src > 1 else n_in, p_begin=0, p_count=0, out_stride=0,
             x_dev=x.data_ptr(), elev_dev=elev_d.data_ptr(), azim_dev=azim_d.data_ptr(),
             az_kind_dev=self.kinds_d.data_ptr() if self.kinds_d is not None else None,
@@ -704,7 +696,6 @@ class DeviceRender:
     def _unfuse(self, stream):
         dev, torch = self.dev, self.torch
         self.fused, self._fused_flag = False, 0
-        self.n_pre = self.job.n_pre = 0
         self.filt = torch.empty((self.n_src * self.n_pts, lib.bas_filter_row_pitch(dev.taps), 2), dtype=torch.float32, device=dev.device)
         self.job.filt_dev = self.filt.data_ptr()
         _cabi.check(lib.bas_ir_synth(dev.bank_pp.data_ptr(), dev.upsampling, dev.taps, self.terms.data_ptr(), self.n_src * self.n_pts,

@@ -49,12 +49,6 @@ int bas_plan_build_inline(const double* diffs_left_dev, const double* diffs_righ
                           const double* elev_host, const double* azim_host, int az_kind_all, long long n_points,
                           bas_term* terms_dev, int* status_dev, long long point_offset, void* stream);
 
-int bas_render_fused_pre(const float* x_dev, long long x_stride, long long n_valid, int n_src, long long n_in, int C, int S, int K,
-                         const bas_term* terms_dev, const float* bank_pp2_dev, int U, const float* filt_dev, int n_pre,
-                         const float* gains_dev, long long p_begin, long long p_count, float* out_dev, long long out_stride, int mix,
-                         float* peaks_dev, int variant, void* workspace_dev, long long workspace_bytes, const bas_route* route,
-                         void* stream);
-
 static inline long long bas_ceil_div(long long a, long long b) { return (a + b - 1) / b; }
 
 // ---- programmatic dependent launch ---------------------------------------------------------------

@@ -133,10 +133,8 @@ static int render_common(const float* x_dev, long long x_stride, long long n_val
                          int C, int S, int K, const float* filt_dev, const bas_term* terms_dev, const float* bank_pp2_dev, int U,
                          const float* gains_dev, long long p_begin, long long p_count, float* out_dev, long long out_stride, int mix,
                          float* peaks_dev, int variant, void* workspace_dev, long long workspace_bytes, void* stream,
-                         const bas_route* route = nullptr, int n_pre = 0) {
-    // fused: plan terms + doubled bank given; filt_dev may then hold ready-made rows for the first n_pre sources
-    const bool fused = terms_dev != nullptr;
-    BAS_CHECK_ARG(n_pre >= 0 && n_pre <= n_src && (n_pre == 0 || (fused && filt_dev)), "n_pre");
+                         const bas_route* route = nullptr) {
+    const bool fused = filt_dev == nullptr;
     if (route && route->n > 1) {
         BAS_CHECK_ARG(mix == 1 && route->table_dev && route->rank >= 0 && route->rank < route->n && route->n <= 32, "route: mixing renders only, rank < n <= 32");
         BAS_CHECK_ARG(route->len > 0 && route->len % 32 == 0 && route->stride >= route->len && route->stride % 4 == 0, "route: slice length / stride");
@@ -161,7 +159,7 @@ static int render_common(const float* x_dev, long long x_stride, long long n_val
     prm.filt_src_stride = (n_in / C + 1) * (long long)prm.pitch;
     prm.gains = gains_dev; prm.p_begin = p_begin; prm.p_end = p_begin + p_count;
     prm.out = out_dev; prm.out_stride = out_stride; prm.mix = mix ? 1 : 0; prm.accumulate = mix == BAS_MIX_ACCUMULATE ? 1 : 0; prm.peaks = peaks_dev; prm.tiles = 0; prm.parts = 1; prm.tmap = 0; prm.box_rows = 0; prm.n_box = 0;
-    prm.terms = reinterpret_cast<const TermDev*>(terms_dev); prm.bank2 = bank_pp2_dev; prm.U = U; prm.nf = 0; prm.n_pre = n_pre;
+    prm.terms = reinterpret_cast<const TermDev*>(terms_dev); prm.bank2 = bank_pp2_dev; prm.U = U; prm.nf = 0;
     const bool routed = route && route->n > 1;
     prm.route_table = routed ? route->table_dev : nullptr; prm.route_n = routed ? route->n : 0; prm.route_rank = routed ? route->rank : 0;
     prm.route_len = routed ? route->len : 1; prm.route_stride = routed ? route->stride : 0;
@@ -171,7 +169,7 @@ static int render_common(const float* x_dev, long long x_stride, long long n_val
     // the tiled kernel works on 32-sample input rows: a subchunk is a whole number of rows (32, 64, ...) or half a row (16)
     const int subs = S == kBlk / 2 ? 2 : 1;
     const bool tiled_ok = (S % kBlk == 0 || S == kBlk / 2) && C % kBlk == 0 && n_valid % 4 == 0 && (reinterpret_cast<uintptr_t>(x_dev) & 15) == 0 &&
-                          ((fused && n_pre == 0) || (reinterpret_cast<uintptr_t>(filt_dev) & 15) == 0) && (n_src == 1 || x_stride % 4 == 0);
+                          (fused || (reinterpret_cast<uintptr_t>(filt_dev) & 15) == 0) && (n_src == 1 || x_stride % 4 == 0);
     if ((base == BAS_RENDER_TILED || fused) && !tiled_ok) {
         bas_set_error("bas_render: tiled kernel needs subchunksize 16 or a multiple of 32, 32 | C, 4 | n_valid, 16-byte aligned signals and filter rows");
         return BAS_E_UNSUPPORTED;
@@ -272,17 +270,6 @@ extern "C" int bas_render_routed(const float* x_dev, long long x_stride, long lo
     BAS_CHECK_ARG(filt_dev || (terms_dev && bank_pp2_dev), "need filter rows, or plan terms and the doubled bank");
     return render_common(x_dev, x_stride, n_valid, n_src, n_in, C, S, K, filt_dev, filt_dev ? nullptr : terms_dev, bank_pp2_dev, U, gains_dev,
                          p_begin, p_count, out_dev, out_stride, 1, peaks_dev, variant, workspace_dev, workspace_bytes, stream, route);
-}
-
-// bas_render_fused / bas_render_routed with ready-made filter rows for the first n_pre sources (bas_step_job.n_pre)
-int bas_render_fused_pre(const float* x_dev, long long x_stride, long long n_valid, int n_src, long long n_in, int C, int S, int K,
-                         const bas_term* terms_dev, const float* bank_pp2_dev, int U, const float* filt_dev, int n_pre,
-                         const float* gains_dev, long long p_begin, long long p_count, float* out_dev, long long out_stride, int mix,
-                         float* peaks_dev, int variant, void* workspace_dev, long long workspace_bytes, const bas_route* route,
-                         void* stream) {
-    BAS_CHECK_ARG(terms_dev && bank_pp2_dev, "null pointer");
-    return render_common(x_dev, x_stride, n_valid, n_src, n_in, C, S, K, n_pre > 0 ? filt_dev : nullptr, terms_dev, bank_pp2_dev, U, gains_dev,
-                         p_begin, p_count, out_dev, out_stride, mix, peaks_dev, variant, workspace_dev, workspace_bytes, stream, route, n_pre);
 }
 
 extern "C" int bas_render_fused_supported(int C, int S) { return (S % kBlk == 0 || S == kBlk / 2) && S >= 1 && C % kBlk == 0 && C % S == 0 ? 1 : 0; }

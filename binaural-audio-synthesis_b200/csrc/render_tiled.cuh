@@ -32,9 +32,6 @@ struct RenderParams {
     const float* bank2;            // polyphase bank with every phase row stored twice: [ear][row][U][2K] (+ padding)
     int U;
     int nf;                        // FUSED: filter-row buffers in shared memory (2: producers run one item ahead)
-    int n_pre;                     // FUSED: sources below n_pre have their filter rows in `filt` already (bas_ir_synth): the
-                                   // producers copy those with one bulk copy instead of gathering them - the gathers are what
-                                   // the producers cannot sustain for every source
     // routed mix (MIX kernels, several GPUs, peer.cu): a finished tile of the local mix is not stored to `out` but
     // into the receive buffer of the rank that owns its stretch of the output, over NVLink:
     //   route_table[owner] + (route_rank * 2 + ear) * route_stride + (p - owner * route_len)
@@ -499,18 +496,6 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
             tile_chunks(it.tile, n_lo, c_first, n_rows);
             const int fb = j % prm.nf;
             if (j >= prm.nf) mbar_wait(empty_f + fb, (unsigned)((j / prm.nf - 1) & 1));      // consumers left the buffer
-            if (it.src < prm.n_pre) {
-                // rows synthesised ahead of the launch: one bulk copy, its bytes counted on the same barrier the gathers use
-                if (ptid == 0) {
-                    const unsigned f_bytes = (unsigned)n_rows * prm.pitch * 8;
-                    mbar_arrive_expect_tx(full_f + fb, f_bytes);
-                    bulk_g2s(fbuf_base + (size_t)fb * g.f_bytes, prm.filt + (long long)it.src * prm.filt_src_stride + c_first * prm.pitch,
-                             f_bytes, full_f + fb);
-                } else {
-                    mbar_arrive(full_f + fb);
-                }
-                continue;
-            }
             asm volatile("bar.sync 2, %0;" ::"r"(PT) : "memory");                            // ... and every producer the table
             const TermDev* tsrc = prm.terms + ((long long)it.src * (n_chunks + 1) + c_first) * kTermsPerRow;
             for (int e = ptid; e < n_rows * kTermsPerRow; e += PT) {

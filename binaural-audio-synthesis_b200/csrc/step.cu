@@ -22,7 +22,6 @@ extern "C" int bas_render_step(const bas_step_job* j, void* stream) {
     const long long n_pts = j->n_in / j->C + 1;
     const long long n_dirs = n_pts * j->n_src;
     const bool fused = (j->flags & BAS_STEP_FUSED) != 0;
-    BAS_CHECK_ARG(j->n_pre >= 0 && j->n_pre <= j->n_src && (j->n_pre == 0 || fused), "n_pre (fused steps only)");
     int* status = j->small_dev;
     float* peaks = reinterpret_cast<float*>(j->small_dev + 2);
     cudaStream_t st = (cudaStream_t)stream;
@@ -35,25 +34,23 @@ extern "C" int bas_render_step(const bas_step_job* j, void* stream) {
             if (int rc = bas_plan_build_range(j->diffs_left_dev, j->diffs_right_dev, j->U, j->K * j->U, j->elev_dev, j->azim_dev,
                                               j->az_kind_dev, j->az_kind_all, n_dirs, j->terms_dev, nullptr, status, 0, 0, st)) return rc;
         }
-        // filter rows in HBM: for every source on the two-kernel path, for the first n_pre sources when fused
-        const long long n_rows_hbm = fused ? (long long)j->n_pre * n_pts : n_dirs;
-        if (n_rows_hbm > 0) {
+        if (!fused) {
             BAS_CHECK_ARG(j->filt_dev && j->bank_pp_dev, "null filter-row scratch or bank");
             BasPdlScope chained(true);
-            if (int rc = bas_ir_synth(j->bank_pp_dev, j->U, j->K, j->terms_dev, n_rows_hbm, BAS_IR_ROWS, j->filt_dev, j->K, st)) return rc;
+            if (int rc = bas_ir_synth(j->bank_pp_dev, j->U, j->K, j->terms_dev, n_dirs, BAS_IR_ROWS, j->filt_dev, j->K, st)) return rc;
         }
     }
     if ((j->flags & BAS_STEP_RENDER) && j->p_count > 0) {
         BasPdlScope chained((j->flags & BAS_STEP_PLAN) != 0);      // a render-only call follows whatever the caller enqueued
         int rc;
-        if (fused)
-            rc = bas_render_fused_pre(j->x_dev, j->x_stride, j->n_valid, j->n_src, j->n_in, j->C, j->S, j->K, j->terms_dev, j->bank_pp2_dev,
-                                      j->U, j->filt_dev, j->n_pre, j->gains_dev, j->p_begin, j->p_count, j->out_dev, j->out_stride, j->mix,
-                                      peaks, j->variant, j->workspace_dev, j->workspace_bytes, j->route, st);
-        else if (j->route && j->route->n > 1)
-            rc = bas_render_routed(j->x_dev, j->x_stride, j->n_valid, j->n_src, j->n_in, j->C, j->S, j->K, j->filt_dev, nullptr, nullptr, j->U,
-                                   j->gains_dev, j->p_begin, j->p_count, j->out_dev, j->out_stride, peaks, j->variant, j->workspace_dev,
-                                   j->workspace_bytes, j->route, st);
+        if (j->route && j->route->n > 1)
+            rc = bas_render_routed(j->x_dev, j->x_stride, j->n_valid, j->n_src, j->n_in, j->C, j->S, j->K, fused ? nullptr : j->filt_dev,
+                                   j->terms_dev, j->bank_pp2_dev, j->U, j->gains_dev, j->p_begin, j->p_count, j->out_dev, j->out_stride,
+                                   peaks, j->variant, j->workspace_dev, j->workspace_bytes, j->route, st);
+        else if (fused)
+            rc = bas_render_fused(j->x_dev, j->x_stride, j->n_valid, j->n_src, j->n_in, j->C, j->S, j->K, j->terms_dev, j->bank_pp2_dev,
+                                  j->U, j->gains_dev, j->p_begin, j->p_count, j->out_dev, j->out_stride, j->mix, peaks, j->variant,
+                                  j->workspace_dev, j->workspace_bytes, st);
         else
             rc = bas_render(j->x_dev, j->x_stride, j->n_valid, j->n_src, j->n_in, j->C, j->S, j->K, j->filt_dev, j->gains_dev,
                             j->p_begin, j->p_count, j->out_dev, j->out_stride, j->mix, peaks, j->variant, j->workspace_dev,

@@ -250,9 +250,7 @@ typedef struct bas_step_job {
     int variant;                  /* bas_render variant */
     int az_kind_all;              /* BAS_AZ_* of every direction when az_kind_dev is NULL */
     int flags;                    /* BAS_STEP_* */
-    int n_pre;                    /* BAS_STEP_FUSED: the first n_pre sources still get their filter rows from a bas_ir_synth
-                                     launch (filt_dev holds n_pre x (n_in/C + 1) rows) and the render kernel copies them; the
-                                     producer warps gather the rest.  0: all rows are gathered in-kernel */
+    int reserved;
     long long n_valid, n_in;      /* samples per source / rounded up to a multiple of C */
     long long x_stride;           /* floats between sources in x_dev */
     long long p_begin, p_count;   /* rendered output range */

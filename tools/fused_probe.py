@@ -59,17 +59,6 @@ for fused in (True, False):
         except Exception as e:
             res['%s tw%d ns%d ctas%d' % ('fused' if fused else 'plain', tw, ns, ctas)] = str(e)[:60]
         del job
-# hybrid: one source in `every` still takes its rows from bas_ir_synth (plan() runs it), the producers gather the rest
-ah.FUSED = True
-for every in (0, 12, 8, 6, 5, 4, 3):
-    ah.FUSED_PRE_EVERY = every
-    job = ah.DeviceRender(torch, bdev, x, n_in, 512, 32, elev, azim, cabi.AZ_F64, mix, 0)
-    t_plan = timed(lambda: job.plan(st))
-    t_render = timed(lambda: job.render(st, 0, n_out, out.data_ptr(), stride))
-    res['fused, 1 source in %d pre-synthesised (n_pre=%d): plan+synth / render / sum' % (every, job.n_pre)] = [
-        round(1e3 * t_plan / n_src, 1), round(1e3 * t_render / n_src, 1), round(1e3 * (t_plan + t_render) / n_src, 1)]
-    del job
-ah.FUSED_PRE_EVERY = 6
 ah.FUSED = False
 job = ah.DeviceRender(torch, bdev, x, n_in, 512, 32, elev, azim, cabi.AZ_F64, mix, 0)
 res['plan+ir_synth (us per source)'] = round(1e3 * timed(lambda: job.plan(st)) / n_src, 1)
