@@ -172,6 +172,8 @@ __host__ __device__ inline size_t tmap_stage_bytes(const TileGeom& g) {
     return (x + g.f_bytes + 1023) / 1024 * 1024;                  // every stage starts on a swizzle atom
 }
 constexpr int kTermsPerRow = 2 * BAS_MAX_TERMS;             // both ears
+// FUSED: a plan term as the producer warps use it - where its K floats start in the doubled bank (tap 0), and its weight
+struct __align__(16) TermPtr { const float* p; float w; int pad; };
 // FUSED kernels keep the input rows (staged by TMA) and the filter rows (synthesised by the producer warps)
 // apart: NS stages of input rows, then nf buffers of filter rows and one term table
 __host__ __device__ inline size_t fused_x_stage_bytes(const TileGeom& g, bool tmap) {
@@ -184,7 +186,7 @@ __host__ __device__ inline size_t tile_smem_bytes(const TileGeom& g, int TW, int
     if (fused) staging = (tmap ? 1024 : (size_t)TW * g.warp_x_bytes) + (size_t)NS * fused_x_stage_bytes(g, tmap);
     else staging = tmap ? 1024 + (size_t)NS * tmap_stage_bytes(g) : (size_t)NS * g.stage_bytes + (size_t)TW * g.warp_x_bytes;
     return kBarBytes + staging + (size_t)((C / kBlk * 8 + 15) / 16 * 16) +
-           (fused ? (size_t)g.f_rows * kTermsPerRow * 8 + (size_t)nf * g.f_bytes : 0) +
+           (fused ? (size_t)g.f_rows * kTermsPerRow * sizeof(TermPtr) + (size_t)nf * g.f_bytes : 0) +
            (parts > 1 ? (size_t)(TW - TS) * kStripeBytes : 0) + (mix ? (size_t)TS * kStripeBytes : 0);
 }
 // FUSED shapes: TW consumer warps + TW producer warps (whole warpgroups of four, as setmaxnreg wants), two input
@@ -356,8 +358,8 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
     float* xw = reinterpret_cast<float*>(after_stages + (size_t)warp * g.warp_x_bytes);          // unused on the tensor-map path
     float* alpha_tab = reinterpret_cast<float*>(after_stages + (tmap ? 0 : (size_t)TW * g.warp_x_bytes));
     unsigned char* after_tab = reinterpret_cast<unsigned char*>(alpha_tab) + (spc * 8 + 15) / 16 * 16;     // room for SUBS = 2
-    int2* term_tab = reinterpret_cast<int2*>(after_tab);     // FUSED: {float offset into bank2, weight bits} per (row, ear, slot)
-    unsigned char* fbuf_base = after_tab + (FUSED ? (size_t)g.f_rows * kTermsPerRow * 8 : 0);       // FUSED: nf filter-row buffers
+    TermPtr* term_tab = reinterpret_cast<TermPtr*>(after_tab);     // FUSED: {start of the term's taps in bank2, weight} per (row, ear, slot)
+    unsigned char* fbuf_base = after_tab + (FUSED ? (size_t)g.f_rows * kTermsPerRow * sizeof(TermPtr) : 0);       // FUSED: nf filter-row buffers
     unsigned char* after_alpha = fbuf_base + (FUSED ? (size_t)prm.nf * g.f_bytes : 0);
     // partial sums of parts 1..P-1 of every stripe: [stripe][part - 1][r][lane] {L,R}
     u64* red = reinterpret_cast<u64*>(after_alpha);
@@ -505,7 +507,9 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
                 const int ph = (prm.U - shift % prm.U) % prm.U;
                 const int adv = (shift + ph) / prm.U;
                 const int off = t.weight != 0.f ? ((ear * BAS_N_DIRECTIONS + row) * prm.U + ph) * K2 + K - adv : 0;
-                term_tab[e] = make_int2(off, __float_as_int(t.weight));
+                TermPtr tp;
+                tp.p = prm.bank2 + off; tp.w = t.weight; tp.pad = 0;
+                term_tab[e] = tp;
             }
             asm volatile("bar.sync 2, %0;" ::"r"(PT) : "memory");
             float2* fsw = reinterpret_cast<float2*>(fbuf_base + (size_t)fb * g.f_bytes);
@@ -515,27 +519,33 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
             const int pw = warp - TW;
             const int pairs = (K + 63) / 64;                         // tap pairs per lane and row
             for (int row = pw; row < n_rows; row += PW) {
-                const int2* tab = term_tab + row * kTermsPerRow;
+                const TermPtr* tab = term_tab + row * kTermsPerRow;
                 float2* dst = fsw + row * prm.pitch;
-                const float* b0 = prm.bank2 + lane;
-                // 64 loads in flight per lane; the second producer warp of the scheduler is in its FMA phase meanwhile
+                // 64 loads in flight per lane; the second producer warp of the scheduler is in its FMA phase meanwhile.  Few
+                // instructions per gathered word matter here: the producers share the schedulers and the FMA pipe with the FIR
+                // blocks.  One 16-byte table read per term gives a ready pointer and the weight; the two taps of a term
+                // are one packed FMA (same fp32 rounding per lane as two scalar ones).
                 for (int pr = 0; pr < pairs; ++pr) {
                     // taps 64 pr + lane and 64 pr + 32 + lane; past the end of the row the loads stay inside the bank's padding
-                    const float* b = b0 + 64 * pr;
-                    float v0[kTermsPerRow], v1[kTermsPerRow];
+                    const size_t idx = (size_t)(64 * pr + lane);
+                    u64 v[kTermsPerRow];
+                    float w[kTermsPerRow];
 #pragma unroll
                     for (int t = 0; t < kTermsPerRow; ++t) {
-                        const float* q = b + tab[t].x;
-                        v0[t] = __ldg(q);
-                        v1[t] = __ldg(q + 32);
+                        const TermPtr tp = tab[t];
+                        const float* q = tp.p + idx;
+                        v[t] = pack2(__ldg(q), __ldg(q + 32));
+                        w[t] = tp.w;
                     }
-                    float l0 = 0.f, r0 = 0.f, l1 = 0.f, r1 = 0.f;
+                    u64 l = 0ull, r = 0ull;                              // {tap m, tap m + 32} per ear
 #pragma unroll
                     for (int t = 0; t < BAS_MAX_TERMS; ++t) {
-                        const float wl = __int_as_float(tab[t].y), wr = __int_as_float(tab[BAS_MAX_TERMS + t].y);
-                        l0 = fmaf(wl, v0[t], l0); r0 = fmaf(wr, v0[BAS_MAX_TERMS + t], r0);
-                        l1 = fmaf(wl, v1[t], l1); r1 = fmaf(wr, v1[BAS_MAX_TERMS + t], r1);
+                        fma2_acc(l, pack2(w[t], w[t]), v[t]);
+                        fma2_acc(r, pack2(w[BAS_MAX_TERMS + t], w[BAS_MAX_TERMS + t]), v[BAS_MAX_TERMS + t]);
                     }
+                    float l0, l1, r0, r1;
+                    unpack2(l, l0, l1);
+                    unpack2(r, r0, r1);
                     const int m = 64 * pr + lane;
                     if (m < K) dst[m] = make_float2(l0, r0);
                     if (m + 32 < K) dst[m + 32] = make_float2(l1, r1);
