@@ -517,38 +517,43 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
             // and takes them two at a time: the table entry of a term is read once for both, the second load is the
             // first address plus 128 bytes.  The terms are summed in slot order per ear, like ir_synth.cu.
             const int pw = warp - TW;
-            const int pairs = (K + 63) / 64;                         // tap pairs per lane and row
             for (int row = pw; row < n_rows; row += PW) {
                 const TermPtr* tab = term_tab + row * kTermsPerRow;
                 float2* dst = fsw + row * prm.pitch;
                 // 64 loads in flight per lane; the second producer warp of the scheduler is in its FMA phase meanwhile.  Few
                 // instructions per gathered word matter here: the producers share the schedulers and the FMA pipe with the FIR
-                // blocks.  One 16-byte table read per term gives a ready pointer and the weight; the two taps of a term
-                // are one packed FMA (same fp32 rounding per lane as two scalar ones).
-                for (int pr = 0; pr < pairs; ++pr) {
-                    // taps 64 pr + lane and 64 pr + 32 + lane; past the end of the row the loads stay inside the bank's padding
-                    const size_t idx = (size_t)(64 * pr + lane);
-                    u64 v[kTermsPerRow];
-                    float w[kTermsPerRow];
+                // blocks.  A lane takes FOUR taps of one ear at a time (tap0, +32, +64, +96): one table read gives a term's
+                // ready pointer, the four loads are that address plus immediates, and two packed FMAs add the term to the
+                // four taps (same fp32 rounding per lane as scalar FMAs, terms in slot order like ir_synth.cu).
+                for (int tap0 = lane; tap0 < K; tap0 += 128) {
+                    u64 acc[2][2];
 #pragma unroll
-                    for (int t = 0; t < kTermsPerRow; ++t) {
-                        const TermPtr tp = tab[t];
-                        const float* q = tp.p + idx;
-                        v[t] = pack2(__ldg(q), __ldg(q + 32));
-                        w[t] = tp.w;
-                    }
-                    u64 l = 0ull, r = 0ull;                              // {tap m, tap m + 32} per ear
+                    for (int ear = 0; ear < 2; ++ear) {
+                        const TermPtr* te = tab + ear * BAS_MAX_TERMS;
+                        u64 v[BAS_MAX_TERMS][2];
 #pragma unroll
-                    for (int t = 0; t < BAS_MAX_TERMS; ++t) {
-                        fma2_acc(l, pack2(w[t], w[t]), v[t]);
-                        fma2_acc(r, pack2(w[BAS_MAX_TERMS + t], w[BAS_MAX_TERMS + t]), v[BAS_MAX_TERMS + t]);
+                        for (int t = 0; t < BAS_MAX_TERMS; ++t) {
+                            // past the end of the row the loads stay inside the bank's padding
+                            const float* q = te[t].p + (size_t)tap0;
+                            v[t][0] = pack2(__ldg(q), __ldg(q + 32));
+                            v[t][1] = pack2(__ldg(q + 64), __ldg(q + 96));
+                        }
+                        u64 a0 = 0ull, a1 = 0ull;
+#pragma unroll
+                        for (int t = 0; t < BAS_MAX_TERMS; ++t) {
+                            const float w = te[t].w;
+                            const u64 ww = pack2(w, w);
+                            fma2_acc(a0, ww, v[t][0]);
+                            fma2_acc(a1, ww, v[t][1]);
+                        }
+                        acc[ear][0] = a0; acc[ear][1] = a1;
                     }
-                    float l0, l1, r0, r1;
-                    unpack2(l, l0, l1);
-                    unpack2(r, r0, r1);
-                    const int m = 64 * pr + lane;
-                    if (m < K) dst[m] = make_float2(l0, r0);
-                    if (m + 32 < K) dst[m + 32] = make_float2(l1, r1);
+                    float l[4], r[4];
+                    unpack2(acc[0][0], l[0], l[1]); unpack2(acc[0][1], l[2], l[3]);
+                    unpack2(acc[1][0], r[0], r[1]); unpack2(acc[1][1], r[2], r[3]);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (tap0 + 32 * i < K) dst[tap0 + 32 * i] = make_float2(l[i], r[i]);
                 }
             }
             const int pad = prm.pitch - K;                           // zero padding taps K .. pitch - 1 of every row
