@@ -619,12 +619,12 @@ def _phase_plan(p0: int, p1: int, n_in: int, chunksize: int, out_bytes_per_sampl
 
 
 # Filter rows: synthesised inside the render kernel by its producer warps (bas_render_fused), or written to HBM
-# first by a separate bas_ir_synth launch (the two-kernel path) - the same rows, bit for bit.  'auto' fuses where
-# it measures faster on B200: up to FUSED_MAX_TAPS taps the producers keep pace with the FIR
-# blocks well enough to win (64 sources mixed at K = 256: 68.6 against 79.9 us per source); at K = 512 the gathers
-# double while the producers' registers do not, and the two-kernel path is ahead.  True / False force either.
+# first by a separate bas_ir_synth launch (the two-kernel path) - the same rows, bit for bit.  'auto' fuses wherever a
+# fused tile shape fits shared memory (bas_render_fused_fits): measured on B200 the fused
+# step is ahead at every tap count tried - per 60 s source, mixing, plan included: K = 100: 38 against 45 us,
+# K = 256: 65 against 80, K = 384: 109 against 117, K = 512 (U = 16): 143 against 153.  True / False force either.
 FUSED = 'auto'
-FUSED_MAX_TAPS = 384
+FUSED_MAX_TAPS = 4096
 
 
 def _want_fused(taps: int) -> bool:
