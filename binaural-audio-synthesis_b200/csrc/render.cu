@@ -285,6 +285,16 @@ extern "C" int bas_render_fused_fits(int K, int C, int S, int mix, int variant) 
     // 1 when bas_render_fused has a tile shape for this geometry (shared memory for the input stages, at least one
     // filter-row buffer and, when mixing, the running sums) - callers decide up front instead of falling back mid-job
     if (K < 1 || !bas_render_fused_supported(C, S) || (variant & 0x3f) == BAS_RENDER_GENERIC || !bas_render_fused_shape(variant)) return 0;
+    // the answer only depends on the arguments (and the device): remember the last one per host thread - the host
+    // pipeline asks once per phase of every make_signal_move_2d call
+    static thread_local int last_key[5] = {0, 0, 0, 0, 0}, last_dev = -1, last_answer = 0;
+    int dev = -1;
+    cudaGetDevice(&dev);
+    if (dev == last_dev && last_key[0] == K && last_key[1] == C && last_key[2] == S && last_key[3] == (mix ? 1 : 0) && last_key[4] == variant) return last_answer;
+    struct Remember {
+        int *key, *dev_slot, *answer_slot, k0, k1, k2, k3, k4, dev, answer = 0;
+        ~Remember() { key[0] = k0; key[1] = k1; key[2] = k2; key[3] = k3; key[4] = k4; *dev_slot = dev; *answer_slot = answer; }
+    } remember{last_key, &last_dev, &last_answer, K, C, S, mix ? 1 : 0, variant, dev};
     const int tw_req = (variant >> 8) & 0xff;
     const int parts_code = (variant >> 28) & 0x7, parts = parts_code ? 1 << (parts_code - 1) : 1;
     const int idx = (mix ? 1 : 0) + 2 + (S == kBlk / 2 ? 4 : 0);
@@ -295,7 +305,7 @@ extern "C" int bas_render_fused_fits(int K, int C, int S, int mix, int variant) 
         for (int i = 0; i < n_shapes; ++i) {
             if (tw_req && shapes[i].tw != tw_req) continue;
             if (shapes[i].tw % parts) continue;
-            if (shapes[i].ctas_per_sm[idx](K, C, pitch, parts, true) > 0 || shapes[i].ctas_per_sm[idx](K, C, pitch, parts, false) > 0) return 1;
+            if (shapes[i].ctas_per_sm[idx](K, C, pitch, parts, true) > 0 || shapes[i].ctas_per_sm[idx](K, C, pitch, parts, false) > 0) { remember.answer = 1; return 1; }
         }
     }
     return 0;
