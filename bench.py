@@ -323,18 +323,23 @@ class Ctx:
         self.dist.all_gather_object(out, obj)
         return out
 
-    def timed(self, fn, steps, warmup, collective=True):
+    def timed(self, fn, steps, warmup, collective=True, after=None):
         """(ms per step, per-step ms list) of fn(i) over `steps` steps after `warmup`: CUDA events on the
-        launching stream, a barrier + synchronize on both sides, max over ranks."""
+        launching stream, a barrier + synchronize on both sides, max over ranks.  `after` (joins work the steps left
+        on other streams) runs inside the timed region, before the closing event."""
         torch = self.torch
         sync = self.barrier if collective else torch.cuda.synchronize
         for i in range(warmup):
             fn(i)
+        if after:
+            after()
         sync()
         marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
         marks[0].record(self.stream)
         for i in range(steps):
             fn(warmup + i)
+            if after and i == steps - 1:
+                after()
             marks[i + 1].record(self.stream)
         sync()
         total = marks[0].elapsed_time(marks[-1])
@@ -530,8 +535,9 @@ def run_mix(ctx, name):
     mix_mode = not weak
     collective = args.collective if (world > 1 and mix_mode) else 'none'
     peer = None
-    sharded = collective == 'peer_sharded'
-    if collective in ('peer', 'peer_sharded'):
+    sharded = collective in ('peer_sharded', 'peer_pipelined')
+    pipelined = collective == 'peer_pipelined'
+    if collective in ('peer', 'peer_sharded', 'peer_pipelined'):
         peer = distributed._peer_mix(n_out, None)
         ok = torch.tensor([1 if peer is not None else 0], dtype=torch.int32, device=ctx.dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
@@ -567,19 +573,27 @@ def run_mix(ctx, name):
             elif collective == 'reduce':
                 works.append(dist.reduce(piece, dst=0, async_op=True))
 
-    def step(i, replicate=None):
+    def step(i, replicate=None, pipeline=None):
         job, out = sets[i % n_sets]
         works = []
+        pipe = peer is not None and (pipelined if pipeline is None else pipeline)
         if job is not None:
             job.plan(st)
-        if peer is not None:
+        if peer is not None and not pipe:
             peer.begin(st)                                # sharded results: the owners have finished with the previous step
-        for pa, pb in segs:
+        for k, (pa, pb) in enumerate(segs):
             if job is not None:
-                job.render(st, pa, pb, out.data_ptr() + 4 * pa, stride, normalise=not mix_mode, route=peer.route if peer is not None else None)
+                # pipelined: the receive buffers of this step's parity (free once the step three back has been summed
+                # everywhere); the last render of the step signals the owners from inside the kernel
+                route = peer.submit_route(st, signal=k == len(segs) - 1) if pipe else peer.route if peer is not None else None
+                job.render(st, pa, pb, out.data_ptr() + 4 * pa, stride, normalise=not mix_mode, route=route)
             if collective in ('all_reduce', 'reduce'):
                 reduce_segment(out, pa, pb, works)        # NCCL stream: ordered after this render, beside the next one
-        if peer is not None:
+        if pipe:
+            # the exchange (wait for all writers, rank-order sum of this rank's slice, wait for all owners) runs on a
+            # side stream beside the plan and render of the next step
+            peer.submit(st, replicate=(not sharded) if replicate is None else replicate, rendered=job is not None)
+        elif peer is not None:
             if job is None:
                 peer.zero_my_blocks()
             # signal, rank-order sum of this rank's slice; replicated: stored on every rank, wait for all slices
@@ -587,10 +601,16 @@ def run_mix(ctx, name):
         for w in works:
             w.wait()
 
+    def drain():
+        """End of a run of steps: the launching stream waits for the exchanges still in flight on the side stream."""
+        if peer is not None:
+            peer.flush(st)
+
     def mix_of(i):
         """The global mix step i left behind (assembled from the ranks' slices when it was left sharded)."""
         if peer is None:
             return sets[i % n_sets][1]
+        peer.flush(st)
         return peer.gather() if sharded else peer.result
 
     def step_late_collective(i):
@@ -613,7 +633,7 @@ def run_mix(ctx, name):
 
     warmup = max(args.warmup, 3)
     with ClockSampler(ctx.local_rank) as clocks:
-        ms_step, per_step = ctx.timed(step, args.steps, warmup)
+        ms_step, per_step = ctx.timed(step, args.steps, warmup, after=drain)
         if len(clocks.samples) < 20:                     # clock evidence only; not part of any reported time
             t_end = time.time() + 0.5
             while time.time() < t_end:
@@ -648,6 +668,12 @@ def run_mix(ctx, name):
                                                           'owner rank\'s receive buffer, then a rank-order reduce kernel per owner; the summed mix is left SHARDED BY '
                                                           'TIME over the ranks (reduce-scatter semantics; csrc/peer.cu) - collective.ms_per_step_replicated is the '
                                                           'all-reduce form',
+                                                          'peer_pipelined': 'fused with the render over NVLink peer memory - every finished tile is stored into its '
+                                                          'owner rank\'s receive buffer (three sets, by step number) and the render\'s last CTA signals the owners; a '
+                                                          'rank-order reduce kernel per owner on a side stream, BESIDE the plan and render of the next step; the summed '
+                                                          'mix is left SHARDED BY TIME over the ranks (reduce-scatter semantics; csrc/peer.cu).  The timed region ends '
+                                                          'when the last step\'s exchange is complete on every rank.  collective.ms_per_step_exchange_not_pipelined / '
+                                                          '_replicated: the exchange inside its own step / all-reduce form',
                                                           'none': 'none (one rank)'}.get(collective, 'NCCL %s per time segment (%d segments)' % (collective, len(segs))))),
                    'value_counts': 'source-sample-pairs/s: every source contributes N_out = %d output pairs per step' % n_out,
                    'l2_policy': 'steps rotate over %d input/output set(s) of %.0f MB per rank (L2: 126 MB)' % (n_sets, set_bytes / 1e6),
@@ -665,10 +691,15 @@ def run_mix(ctx, name):
         ms_nocomm, _ = ctx.timed(lambda i: (sets[i % n_sets][0].plan(st) if sets[i % n_sets][0] else None, render_only(i)), max(5, args.steps // 2), 3)
         ms_repl = None
         if peer is not None:
-            ms_repl, _ = ctx.timed(lambda i: step(i, replicate=True), max(5, args.steps // 2), 3)
+            ms_repl, _ = ctx.timed(lambda i: step(i, replicate=True), max(5, args.steps // 2), 3, after=drain)
+            ms_serial = None
+            if pipelined:
+                ms_serial, _ = ctx.timed(lambda i: step(i, pipeline=False), max(5, args.steps // 2), 3, after=drain)
             if sharded:
                 step(0)                                  # leave the buffers in the default (sharded) state
+                drain()
         line['collective'] = {'op': collective, 'bytes_per_step': int(8 * n_out), 'ms_per_step': ms_step, 'ms_per_step_replicated': ms_repl,
+                              'ms_per_step_exchange_not_pipelined': ms_serial,
                               'ms_per_step_with_one_nccl_all_reduce_at_the_end': ms_late, 'ms_per_step_without_exchange': ms_nocomm,
                               'exposed_ms': ms_step - ms_nocomm}
 
@@ -902,7 +933,7 @@ def run_hour(ctx):
 
     warmup = max(args.warmup, 3)
     with ClockSampler(ctx.local_rank) as clocks:
-        ms_step, per_step = ctx.timed(step, args.steps, warmup)
+        ms_step, per_step = ctx.timed(step, args.steps, warmup, after=drain)
     assert cabi.decode_status(job.small.cpu().numpy())[0] == 0
     per_rank = ctx.gather_objects({'rank': rank, 'mean_ms': float(np.mean(per_step)), 'outputs': int(p1 - p0)})
     # parity: every seam against rank 0 rendering a window across it alone; the first window against the oracle
@@ -957,9 +988,10 @@ def main():
     ap.add_argument('--config', default='mix64', help='mix64 (default) | single | hour | stress1024, or SURVEY.md config number 2..5')
     ap.add_argument('--variant', type=lambda v: int(v, 0), default=0, help='bas_render variant (tuning)')
     ap.add_argument('--segments', type=int, default=0, help='time segments of the mix (0: distributed.MIX_SEGMENTS)')
-    ap.add_argument('--collective', default='peer_sharded', choices=['peer_sharded', 'peer', 'all_reduce', 'reduce'],
-                    help='sum of the per-rank mixes: fused with the render over peer memory, result left sharded by time (default) or '
-                         'replicated on every rank (peer), or NCCL after the render')
+    ap.add_argument('--collective', default='peer_pipelined', choices=['peer_pipelined', 'peer_sharded', 'peer', 'all_reduce', 'reduce'],
+                    help='sum of the per-rank mixes: fused with the render over peer memory, result left sharded by time, the exchange of a '
+                         'step beside the render of the next (default) or inside its own step (peer_sharded), or replicated on every rank '
+                         '(peer), or NCCL after the render')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-single', action='store_true', help='skip the single_source block')
     args = ap.parse_args()

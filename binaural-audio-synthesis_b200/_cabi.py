@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libbas_b200.so')
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 N_DIRECTIONS = 187
 MAX_TERMS = 16
 AZ_PYFLOAT, AZ_F64, AZ_F32 = 0, 1, 2
@@ -70,7 +70,8 @@ STEP_PLAN, STEP_RENDER, STEP_NORMALISE, STEP_FUSED = 1, 2, 4, 8
 
 class Route(C.Structure):
     """bas_route (include/bas_b200.h)."""
-    _fields_ = [('table_dev', C.c_void_p), ('n', C.c_int), ('rank', C.c_int), ('len', C.c_longlong), ('stride', C.c_longlong)]
+    _fields_ = [('table_dev', C.c_void_p), ('n', C.c_int), ('rank', C.c_int), ('len', C.c_longlong), ('stride', C.c_longlong),
+                ('arrive_ptrs_dev', C.c_void_p), ('arrive_counter_dev', C.c_void_p), ('arrive_epoch', C.c_uint), ('reserved', C.c_uint)]
 
 
 class StepJob(C.Structure):
@@ -123,6 +124,8 @@ def _load():
         'bas_peer_signal': ([vp, i, i, C.c_uint, vp], i),
         'bas_peer_reduce': ([vp, i, ll, ll, vp, i, ll, ll, vp, C.c_uint, vp, i, vp, vp, vp], i),
         'bas_peer_wait': ([vp, i, C.c_uint, vp], i),
+        'bas_render_set_trace': ([vp], i),
+        'bas_peer_stream_wait': ([vp, i, C.c_uint, vp], i),
         'bas_render_workspace_bytes': ([], ll),
         'bas_normalise': ([vp, ll, vp, vp], i),
         'bas_peak': ([vp, ll, vp, vp], i),

@@ -19,6 +19,7 @@
 // Memory: caller-owned symmetric buffers (torch.distributed._symmetric_memory supplies the peer mappings;
 // this library never allocates).  All waits are bounded by elapsed time (trap instead of hanging the GPU).
 #include "bas_internal.cuh"
+#include <cuda.h>
 
 namespace {
 
@@ -112,6 +113,35 @@ extern "C" int bas_peer_signal(unsigned* const* flag_ptrs_dev, int n, int slot, 
 extern "C" int bas_peer_wait(const unsigned* flags_dev, int n, unsigned epoch, void* stream) {
     BAS_CHECK_ARG(flags_dev && n >= 1 && n <= 32, "bad arguments");
     BAS_CUDA(bas_launch(bas_peer_wait_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, flags_dev, n, epoch));
+    return 0;
+}
+
+// Stream-ordered wait without a resident kernel: n cuStreamWaitValue32(GEQ) operations - the stream's front end
+// polls the flags, no SM is held while a peer is late (a spinning bas_peer_wait / bas_peer_reduce CTA would keep a
+// persistent render CTA of the next step off its SM).  GEQ is the same wrap-safe comparison as wait_reached.
+typedef CUresult (*StreamWaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static StreamWaitValue32Fn stream_wait_fn() {
+    static StreamWaitValue32Fn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (getenv("BAS_NO_STREAM_WAIT")) return (StreamWaitValue32Fn) nullptr;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return (StreamWaitValue32Fn) nullptr;
+        }
+        return (StreamWaitValue32Fn)p;
+    }();
+    return fn;
+}
+
+extern "C" int bas_peer_stream_wait(const unsigned* flags_dev, int n, unsigned epoch, void* stream) {
+    BAS_CHECK_ARG(flags_dev && n >= 1 && n <= 32, "bad arguments");
+    StreamWaitValue32Fn fn = stream_wait_fn();
+    if (!fn) { bas_set_error("bas_peer_stream_wait: cuStreamWaitValue32 is not available"); return BAS_E_UNSUPPORTED; }
+    for (int w = 0; w < n; ++w) {
+        const CUresult r = fn((CUstream)stream, (CUdeviceptr)(uintptr_t)(flags_dev + w), epoch, CU_STREAM_WAIT_VALUE_GEQ);
+        if (r != CUDA_SUCCESS) { bas_set_error("bas_peer_stream_wait: cuStreamWaitValue32 failed (%d)", (int)r); return BAS_E_UNSUPPORTED; }
+    }
     return 0;
 }
 

@@ -249,3 +249,16 @@ extern "C" int bas_probe_block(int ctas_per_sm, int blocks, int iters, float* si
     BAS_LAUNCH_CHECK();
     return 0;
 }
+
+// ---- time stamps in stream order (tools/peer_cost_probe.py: where do the kernels of a step run?) ----
+namespace {
+__global__ void bas_probe_stamp_kernel(unsigned long long* slot) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    *slot = t;
+}
+}  // namespace
+extern "C" int bas_probe_stamp(unsigned long long* slot_dev, void* stream) {
+    bas_probe_stamp_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(slot_dev);
+    return (int)cudaGetLastError();
+}

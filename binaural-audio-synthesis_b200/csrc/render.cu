@@ -129,6 +129,10 @@ bas_normalise_kernel(float* __restrict__ v, long long n, const float* __restrict
 // shape (tuning sweeps; unknown shapes return BAS_E_UNSUPPORTED).
 // filt_dev: filter rows written by bas_ir_synth(BAS_IR_ROWS); or, fused, terms_dev + bank_pp2_dev + U: the
 // tiled kernel synthesises the rows itself.
+// diagnostics: per-CTA time stamps of the tiled kernel (tools/cta_trace.py)
+static unsigned long long* g_render_trace = nullptr;
+extern "C" int bas_render_set_trace(unsigned long long* trace_dev) { g_render_trace = trace_dev; return 0; }
+
 static int render_common(const float* x_dev, long long x_stride, long long n_valid, int n_src, long long n_in,
                          int C, int S, int K, const float* filt_dev, const bas_term* terms_dev, const float* bank_pp2_dev, int U,
                          const float* gains_dev, long long p_begin, long long p_count, float* out_dev, long long out_stride, int mix,
@@ -139,6 +143,7 @@ static int render_common(const float* x_dev, long long x_stride, long long n_val
         BAS_CHECK_ARG(mix == 1 && route->table_dev && route->rank >= 0 && route->rank < route->n && route->n <= 32, "route: mixing renders only, rank < n <= 32");
         BAS_CHECK_ARG(route->len > 0 && route->len % 32 == 0 && route->stride >= route->len && route->stride % 4 == 0, "route: slice length / stride");
         BAS_CHECK_ARG(route->len * route->n >= p_begin + p_count, "route: the slices do not cover the output");
+        BAS_CHECK_ARG(!route->arrive_ptrs_dev || route->arrive_counter_dev, "route: arrival signal without a counter");
     }
     BAS_CHECK_ARG(x_dev && out_dev && (filt_dev || (terms_dev && bank_pp2_dev && U >= 1)), "null pointer");
     BAS_CHECK_ARG(n_src >= 1, "n_src");
@@ -163,6 +168,9 @@ static int render_common(const float* x_dev, long long x_stride, long long n_val
     const bool routed = route && route->n > 1;
     prm.route_table = routed ? route->table_dev : nullptr; prm.route_n = routed ? route->n : 0; prm.route_rank = routed ? route->rank : 0;
     prm.route_len = routed ? route->len : 1; prm.route_stride = routed ? route->stride : 0;
+    prm.arrive_ptrs = routed ? route->arrive_ptrs_dev : nullptr; prm.arrive_counter = routed ? route->arrive_counter_dev : nullptr;
+    prm.arrive_epoch = routed ? route->arrive_epoch : 0u;
+    prm.trace = g_render_trace;
 
     const int base = variant & 0x3f;
     BAS_CHECK_ARG(base == BAS_RENDER_AUTO || base == BAS_RENDER_GENERIC || base == BAS_RENDER_TILED, "variant");

@@ -38,6 +38,13 @@ struct RenderParams {
     float* const* route_table;     // device array of route_n peer-mapped receive buffers, or NULL
     int route_n, route_rank;
     long long route_len, route_stride;
+    // ... and, when arrive_ptrs is set, the last CTA of the launch to finish tells every rank "the tiles of rank
+    // route_rank have landed" (flag[route_rank] = arrive_epoch on every peer; bas_peer_signal folded into the render)
+    unsigned* const* arrive_ptrs;  // device array of route_n peer-mapped flag arrays, or NULL
+    unsigned* arrive_counter;      // CTAs of this launch that have finished (zero between launches)
+    unsigned arrive_epoch;
+    // diagnostics (bas_render_set_trace; NULL in normal use): per CTA {start ns, end ns, SM id, items}
+    unsigned long long* trace;
 };
 
 __device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
@@ -390,6 +397,11 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
     // stream; the filter rows / plan terms it wrote are read only from here on
     bas_grid_launch_dependents();
     bas_grid_dependency_wait();
+    if (prm.trace != nullptr && tid == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        prm.trace[4 * blockIdx.x] = global_ns(); prm.trace[4 * blockIdx.x + 2] = smid;
+    }
 
     // item j of this CTA (32-bit arithmetic: the host keeps slice counts below 2^31)
     auto item_info = [&](int j) {
@@ -790,6 +802,24 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
             }
 #pragma unroll
             for (int r = 0; r < kBlk; ++r) acc[r] = 0ull;
+        }
+    }
+    if (prm.trace != nullptr && tid == 0) { prm.trace[4 * blockIdx.x + 1] = global_ns(); prm.trace[4 * blockIdx.x + 3] = (unsigned long long)n_items; }
+    if (MIX && prm.arrive_ptrs != nullptr) {
+        // routed mix: every routed store of this CTA is ordered before its count, every count before the last CTA's
+        // signal - a peer that reads the flag (ld.acquire.sys, peer.cu) then finds all tiles of this launch in place
+        __threadfence_system();
+        cta_barrier(TW * 32);
+        if (warp == 0) {
+            unsigned last = 0;
+            if (lane == 0) last = atomicAdd(prm.arrive_counter, 1u) == gridDim.x - 1 ? 1u : 0u;
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (last) {
+                if (lane == 0) *prm.arrive_counter = 0;              // ready for the next launch
+                __threadfence_system();
+                if (lane < prm.route_n)
+                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(prm.arrive_ptrs[lane] + prm.route_rank), "r"(prm.arrive_epoch) : "memory");
+            }
         }
     }
 }

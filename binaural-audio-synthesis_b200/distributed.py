@@ -61,15 +61,26 @@ def mix_segments(n_out: int, n_segments: int = None):
 
 class PeerMix:
     """Sum of the per-rank mixes over peer memory, fused with the render (csrc/peer.cu): symmetric buffers of
-    this rank - a receive block per writer for the slice of the output this rank owns, the full result, and the
+    this rank - a receive block per writer for the slice of the output this rank owns, the result, and the
     flags - with every peer's mapping of them (torch.distributed._symmetric_memory is the plumbing; all
     arithmetic and all signalling is in libbas_b200.so).  One instance per (group, output length); reusable
-    step after step.
+    step after step.  Receive and result buffers exist DEPTH times (step number modulo DEPTH), for the pipelined form.
 
-        route = peer.route                     -> DeviceRender.render(..., route=route)
-        peer.finish(stream)                    -> signal, reduce (rank order: deterministic), wait
-        peer.result[:, :n_out]                 -> the full mix on every rank
+    One step at a time:
+        peer.begin(stream); DeviceRender.render(..., route=peer.route); peer.finish(stream)
+        peer.result[:, :n_out]                 -> the full mix on every rank (replicate=True), or this rank's slice
+
+    Pipelined, for a stream of steps (batches): the exchange of step i runs on a side stream while the main stream
+    plans and renders steps i + 1 and i + 2 into the other receive buffers (a persistent render fills every SM, so the
+    reduce kernel of step i usually runs between two renders, beside the plan kernel; the waits for the peers are
+    stream memory operations and hold no SM) -
+        route = peer.submit_route()            -> DeviceRender.render(..., route=route): the render's last CTA signals
+        peer.submit(stream, replicate=False)   -> side stream: wait for all writers, rank-order sum, wait for all owners
+        ...                                       (the next steps)
+        peer.flush(stream)                     -> `stream` waits for every submitted exchange; peer.result = the latest
     """
+
+    DEPTH = 3            # sets of receive / result buffers: the exchange of step i may still run while step i + 2 renders
 
     def __init__(self, n_out: int, group=None):
         import torch
@@ -79,6 +90,7 @@ class PeerMix:
         self.torch, self._cabi = torch, _cabi
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         device = torch.device('cuda', torch.cuda.current_device())
+        self.device = device
         n = self.world
         self.n_out = n_out
         self.slice_len = (-(-n_out // n) + _SEGMENT_ALIGN - 1) // _SEGMENT_ALIGN * _SEGMENT_ALIGN
@@ -86,62 +98,166 @@ class PeerMix:
         self.result_stride = (n_out + 3) // 4 * 4
         recv_floats = n * 2 * self.stride
         result_floats = 2 * self.result_stride
-        flag_words = 64 * 3                                         # arrived[n] | done[n] | counter, a cache line apart
-        self.buf = symm.empty(recv_floats + result_floats + flag_words, dtype=torch.float32, device=device)
+        flag_words = 64 * 4                      # arrived[n] | done[n] | reduce counter | render counter, a cache line apart
+        d = self.DEPTH
+        self.buf = symm.empty(d * (recv_floats + result_floats) + flag_words, dtype=torch.float32, device=device)
         self.buf.zero_()
         self.handle = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
         torch.cuda.synchronize()
         dist.barrier(group)                                         # every rank's flags are zero before anyone signals
         bases = [int(p) for p in self.handle.buffer_ptrs]
-        off_result, off_flags = 4 * recv_floats, 4 * (recv_floats + result_floats)
+        self._recv_floats = recv_floats
+        off_recv = [4 * recv_floats * k for k in range(d)]
+        off_result = [4 * (d * recv_floats + result_floats * k) for k in range(d)]
+        off_flags = 4 * d * (recv_floats + result_floats)
 
         def table(offset):
             return torch.tensor([b + offset for b in bases], dtype=torch.int64, device=device)
-        self._recv_ptrs = table(0)
-        self._result_ptrs = table(off_result)
+        self._recv_ptrs = [table(o) for o in off_recv]
+        self._result_ptrs = [table(o) for o in off_result]
         self._arrived_ptrs = table(off_flags)
         self._done_ptrs = table(off_flags + 256)
         base = self.buf.data_ptr()
-        self._recv, self._arrived, self._done, self._counter = base, base + off_flags, base + off_flags + 256, base + off_flags + 512
-        self.result = self.buf[recv_floats:recv_floats + result_floats].view(2, self.result_stride)
-        self._own_result_ptr = torch.tensor([bases[self.rank] + off_result], dtype=torch.int64, device=device)
-        self.route = _cabi.Route(table_dev=self._recv_ptrs.data_ptr(), n=n, rank=self.rank, len=self.slice_len, stride=self.stride)
+        self._recv = [base + o for o in off_recv]
+        self._arrived, self._done = base + off_flags, base + off_flags + 256
+        self._counter, self._render_counter = base + off_flags + 512, base + off_flags + 768
+        self.results = [self.buf[d * recv_floats + result_floats * k:d * recv_floats + result_floats * (k + 1)].view(2, self.result_stride)
+                        for k in range(d)]
+        self.result = self.results[0]
+        self._own_result_ptr = [torch.tensor([bases[self.rank] + o], dtype=torch.int64, device=device) for o in off_result]
+        self._routes = [_cabi.Route(table_dev=self._recv_ptrs[k].data_ptr(), n=n, rank=self.rank, len=self.slice_len, stride=self.stride)
+                        for k in range(d)]
+        self._signal_routes = [_cabi.Route(table_dev=self._recv_ptrs[k].data_ptr(), n=n, rank=self.rank, len=self.slice_len, stride=self.stride,
+                                           arrive_ptrs_dev=self._arrived_ptrs.data_ptr(), arrive_counter_dev=self._render_counter)
+                               for k in range(d)]
+        self.route = self._routes[0]
         self.epoch = 0
+        self._latest = 0
         self._pending_wait = False
+        self._stream_wait_ok = True
+        self._side = torch.cuda.Stream(device=device, priority=-1)
+        self._rendered = torch.cuda.Event()
+        self._exchanged = [None] * d                                  # per parity: event "exchange of the last step of this parity complete"
         begin = self.rank * self.slice_len
         self.slice = (begin, max(0, min(n_out, begin + self.slice_len) - begin))      # this rank's stretch of the output
 
-    def zero_my_blocks(self):
+    def _stream(self, handle):
+        """torch's view of a raw stream handle.  Handle 0 is the default stream: ExternalStream(0) would NOT wrap it
+        (torch treats a null pointer as 'no stream given' and takes a fresh one from its pool)."""
+        torch = self.torch
+        return torch.cuda.default_stream(self.device) if not handle else torch.cuda.ExternalStream(handle, device=self.device)
+
+    def zero_my_blocks(self, parity=0):
         """A rank without sources still owes every owner its (all-zero) partial slice."""
         torch = self.torch
         for o in range(self.world):
-            block = self.handle.get_buffer(o, (2 * self.stride,), torch.float32, self.rank * 2 * self.stride)
+            block = self.handle.get_buffer(o, (2 * self.stride,), torch.float32, parity * self._recv_floats + self.rank * 2 * self.stride)
             block.zero_()
 
     def begin(self, stream):
         """Before a routed render: if the previous step left its result sharded, wait until every owner has finished
         summing that step's slices - only then may this rank's tiles overwrite the owners' receive buffers."""
+        self.flush(stream)
         if self._pending_wait:
             self._cabi.check(self._cabi.lib.bas_peer_wait(self._done, self.world, self.epoch & 0xffffffff, stream), 'bas_peer_wait')
             self._pending_wait = False
+
+    def _reduce(self, parity, e, replicate, fold_signal, stream):
+        cabi, lib = self._cabi, self._cabi.lib
+        n = self.world
+        begin, valid = self.slice
+        table = self._result_ptrs[parity] if replicate else self._own_result_ptr[parity]
+        cabi.check(lib.bas_peer_reduce(self._recv[parity], n, self.stride, valid, table.data_ptr(), n if replicate else 1, self.result_stride, begin,
+                                       self._arrived, e, self._done_ptrs.data_ptr(), self.rank, self._counter,
+                                       self._arrived_ptrs.data_ptr() if fold_signal else None, stream), 'bas_peer_reduce')
 
     def finish(self, stream, replicate=True):
         """After this rank's routed render: signal, sum this rank's slice in rank order.  replicate=True: the sum is
         stored into every rank's result buffer and the call waits for all slices - `result` holds the full mix on
         every rank (an all-reduce).  replicate=False: the sum stays here, `result[:, slice]` is this rank's stretch of
         the mix (a reduce-scatter; `gather()` assembles it) and the wait moves to the next `begin`."""
-        cabi, lib = self._cabi, self._cabi.lib
         self.epoch += 1
-        n, e = self.world, self.epoch & 0xffffffff
-        begin, valid = self.slice
-        table = self._result_ptrs if replicate else self._own_result_ptr
-        cabi.check(lib.bas_peer_reduce(self._recv, n, self.stride, valid, table.data_ptr(), n if replicate else 1, self.result_stride, begin,
-                                       self._arrived, e, self._done_ptrs.data_ptr(), self.rank, self._counter,
-                                       self._arrived_ptrs.data_ptr(), stream), 'bas_peer_reduce')
+        e = self.epoch & 0xffffffff
+        self._reduce(0, e, replicate, True, stream)
+        self.result = self.results[0]
         if replicate:
-            cabi.check(lib.bas_peer_wait(self._done, n, e, stream), 'bas_peer_wait')
+            self._cabi.check(self._cabi.lib.bas_peer_wait(self._done, self.world, e, stream), 'bas_peer_wait')
         else:
             self._pending_wait = True
+
+    # ---- pipelined form ----------------------------------------------------------------------------
+    def submit_route(self, stream, signal=True):
+        """The route of the step about to be rendered on `stream` (cuda stream handle): the receive buffers of its
+        parity, which `stream` may write once every owner has summed the step that used them last.  signal=True (the
+        step's LAST routed render): the render kernel itself tells the owners when this rank's tiles have landed."""
+        if self._pending_wait:                                       # a sharded step of the one-at-a-time form came before
+            self.begin(stream)
+        parity = (self.epoch + 1) % self.DEPTH
+        ev = self._exchanged[parity]
+        if ev is not None:
+            self._stream(stream).wait_event(ev)
+            self._exchanged[parity] = None
+        if not signal:
+            return self._routes[parity]
+        route = self._signal_routes[parity]
+        route.arrive_epoch = (self.epoch + 1) & 0xffffffff
+        return route
+
+    def submit(self, stream, replicate=False, rendered=True):
+        """After the step's routed renders on `stream`: its exchange goes to the side stream - wait for every writer, sum
+        this rank's slice in rank order into results[parity] (of every rank: replicate), wait until every owner is
+        done.  `stream` is not held up; flush() or the submit_route() DEPTH steps later joins it."""
+        torch, cabi, lib = self.torch, self._cabi, self._cabi.lib
+        self.epoch += 1
+        e = self.epoch & 0xffffffff
+        parity = self.epoch % self.DEPTH
+        if not rendered:                                            # no sources here: zero blocks, explicit signal
+            with torch.cuda.stream(self._stream(stream)):
+                self.zero_my_blocks(parity)
+            cabi.check(lib.bas_peer_signal(self._arrived_ptrs.data_ptr(), self.world, self.rank, e, stream), 'bas_peer_signal')
+        self._rendered.record(self._stream(stream))
+        self._side.wait_event(self._rendered)
+        side = self._side.cuda_stream
+        # both waits as stream memory operations where the driver offers them: no CTA sits on an SM while a peer is late
+        # (the reduce kernel's own check of the arrival flags then passes at once)
+        self._side_wait(self._arrived, e)
+        self._reduce(parity, e, replicate, False, side)
+        self._side_wait(self._done, e)
+        ev = torch.cuda.Event()
+        ev.record(self._side)
+        self._exchanged[parity] = ev
+        self._latest = parity
+        return parity, ev
+
+    def _side_wait(self, flags, e):
+        cabi, lib = self._cabi, self._cabi.lib
+        side = self._side.cuda_stream
+        if self._stream_wait_ok:
+            rc = lib.bas_peer_stream_wait(flags, self.world, e, side)
+            if rc == 0:
+                return
+            if rc != cabi.E_UNSUPPORTED:
+                cabi.check(rc, 'bas_peer_stream_wait')
+            self._stream_wait_ok = False
+        cabi.check(lib.bas_peer_wait(flags, self.world, e, side), 'bas_peer_wait')
+
+    def collect(self, ticket, stream):
+        """The result buffer (2, result_stride) of the step submit() returned `ticket` for, once `stream` has waited for
+        its exchange.  Valid until DEPTH - 1 further steps have been submitted."""
+        parity, ev = ticket
+        self._stream(stream).wait_event(ev)
+        return self.results[parity]
+
+    def flush(self, stream):
+        """`stream` waits for every submitted exchange; `result` is then the mix of the last submitted step."""
+        ext = None
+        for k in range(self.DEPTH):
+            if self._exchanged[k] is not None:
+                ext = ext or self._stream(stream)
+                ext.wait_event(self._exchanged[k])
+                self._exchanged[k] = None
+        if ext is not None:
+            self.result = self.results[self._latest]
 
     def gather(self, group=None):
         """The full (2, n_out) mix on every rank from the sharded result (torch all_gather of the slices)."""
@@ -316,6 +432,93 @@ def render_mix_by_source(signals, chunksize, subchunksize, elev_azim_functions, 
     if dst is None or rank == dst:
         return result
     return None
+
+
+def render_mix_stream(batches, chunksize, subchunksize, bank, group=None, replicate=True):
+    """A STREAM of batches of sources, each mixed over the ranks of `group` like render_mix_by_source(..., normalise=False),
+    the exchange of a batch running beside the plan and render of the next one (PeerMix, pipelined form).
+
+    batches: iterable of (signals, elev_azim_functions) - this rank's share of every batch: a CUDA float32 tensor
+    (n_local >= 1, N), the same shape for every batch, and its trajectories (as render_sources takes them).
+    Yields one (2, N_out) CUDA tensor per batch, in order, each after the NEXT batch has been enqueued (the last one
+    after the loop).  replicate=True: the full mix on every rank; False: a reduce-scatter - only the columns
+    [rank * slice_len, (rank + 1) * slice_len) hold this rank's stretch of the sum.  The tensor is a view of the
+    exchange buffers, valid until two more batches have been drawn from the generator: copy it to keep it.  No normalisation
+    (apply_hrtf.py:462-464 is per source).  A trajectory error on any rank raises on every rank."""
+    import torch
+    import torch.distributed as dist
+    from . import apply_hrtf as ah
+    from ._cabi import decode_status, RENDER_AUTO
+    device = torch.device('cuda', torch.cuda.current_device())
+    world = dist.get_world_size(group)
+    main = torch.cuda.current_stream()
+    st = main.cuda_stream
+    dev = ah._device_bank(bank)
+    state = {'peer': None, 'asked': False, 'scratch': None}
+
+    def enqueue(signals, trajs):
+        if not (isinstance(signals, torch.Tensor) and signals.is_cuda and signals.dtype == torch.float32 and signals.dim() == 2 and len(signals)):
+            raise ValueError('render_mix_stream takes CUDA float32 signals (n_local >= 1, N)')
+        n_local, n = signals.shape
+        k, n_in, n_out = ah.render_geometry(n, chunksize, subchunksize, bank)
+        stride = (n_out + 3) // 4 * 4
+        if signals.is_contiguous() and n == n_in:
+            x = signals
+        else:
+            x = torch.zeros((n_local, n_in), dtype=torch.float32, device=device)
+            x[:, :n].copy_(signals)
+        elev, azim, kinds = ah._directions(trajs, n_local, n_in, chunksize)
+        elev_d = torch.as_tensor(elev, dtype=torch.float64).to(device).contiguous().reshape(-1)
+        azim_d = torch.as_tensor(azim, dtype=torch.float64).to(device).contiguous().reshape(-1)
+        if elev_d.numel() != n_local * (n_in // chunksize + 1) or azim_d.numel() != elev_d.numel():
+            raise ValueError('trajectories must give %d directions per source' % (n_in // chunksize + 1))
+        job = ah.DeviceRender(torch, dev, x, n_in, chunksize, subchunksize, elev_d, azim_d, kinds, True, RENDER_AUTO)
+        job.plan(st)
+        if world > 1 and not state['asked']:
+            peer = _peer_mix(n_out, group)
+            ok = torch.tensor([1 if peer is not None else 0], dtype=torch.int32, device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)           # all ranks take the same path
+            state['peer'], state['asked'] = (peer if int(ok) else None), True
+        peer = state['peer']
+        if peer is not None:
+            if state['scratch'] is None:
+                state['scratch'] = torch.zeros((2, stride), dtype=torch.float32, device=device)     # never written: every tile has an owner
+            job.render(st, 0, n_out, state['scratch'].data_ptr(), stride, route=peer.submit_route(st))
+            ticket = peer.submit(st, replicate=replicate)
+            out = None
+        else:
+            out = torch.zeros((2, stride), dtype=torch.float32, device=device)
+            job.render(st, 0, n_out, out.data_ptr(), stride)
+            ticket = None
+        flag = (job.small[:1] != 0).to(torch.int32)
+        work = None
+        if world > 1:
+            if peer is None:
+                dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+            work = dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group, async_op=True)
+        return job, ticket, out, flag, work, n_out
+
+    def collect(entry):
+        job, ticket, out, flag, work, n_out = entry
+        if work is not None:
+            work.wait()
+        if int(flag):                                                # the batch is a step old: this wait costs the device nothing
+            bits, index = decode_status(job.small.cpu().numpy())
+            if bits:
+                ah._raise_plan_error(bits, ' (trajectory point %d of source %d)' % (index % job.n_pts, index // job.n_pts))
+            raise ah.BasError('render_mix_stream: a trajectory failed on another rank')
+        if ticket is not None:
+            out = state['peer'].collect(ticket, st)
+        return out[:, :n_out]
+
+    pending = None
+    for signals, trajs in batches:
+        entry = enqueue(signals, trajs)
+        if pending is not None:
+            yield collect(pending)
+        pending = entry
+    if pending is not None:
+        yield collect(pending)
 
 
 def _render_mix_injected(torch, dist, signals, chunksize, subchunksize, elev_azim_functions, bank, group, dst, render, normalise):

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define BAS_ABI_VERSION 4
+#define BAS_ABI_VERSION 5
 
 #define BAS_N_DIRECTIONS 187      /* rows of the measurement grid, sphere.py:127-315 */
 #define BAS_MAX_TERMS 16          /* merged gather terms per ear per trajectory point */
@@ -219,6 +219,12 @@ typedef struct bas_route {
     int n, rank;                  /* ranks; this rank */
     long long len;                /* output samples per slice (multiple of 32); n * len >= N_out */
     long long stride;             /* floats between the ear rows of a receive block (>= len, multiple of 4) */
+    /* optional: fold bas_peer_signal into the render - the last CTA of the launch to finish stores arrive_epoch
+     * into flag [rank] of every rank's arrived-array.  Set it on the LAST routed render of a step only. */
+    unsigned* const* arrive_ptrs_dev;   /* device array: arrived-flags of every rank (peer-mapped), or NULL */
+    unsigned* arrive_counter_dev;       /* one word of this rank, zeroed once; the launches of a stream share it */
+    unsigned arrive_epoch;
+    unsigned reserved;
 } bas_route;
 int bas_render_routed(const float* x_dev, long long x_stride, long long n_valid, int n_src, long long n_in,
                       int C, int S, int K, const float* filt_dev, const bas_term* terms_dev, const float* bank_pp2_dev, int U,
@@ -231,6 +237,9 @@ int bas_peer_reduce(const float* recv_dev, int n, long long stride, long long va
                     unsigned* const* done_ptrs_dev, int rank, unsigned* counter_dev, unsigned* const* arrive_ptrs_dev,
                     void* stream);
 int bas_peer_wait(const unsigned* flags_dev, int n, unsigned epoch, void* stream);
+/* The same wait as n stream memory operations (cuStreamWaitValue32, >=): nothing is resident on the SMs while a peer
+ * is late.  BAS_E_UNSUPPORTED when the driver does not offer it: use bas_peer_wait. */
+int bas_peer_stream_wait(const unsigned* flags_dev, int n, unsigned epoch, void* stream);
 
 /* ---- one render step as one call: apply_hrtf.py:429-435 feeding :438-453 and :459-464 ----------
  * bas_render_step enqueues, on `stream`: [BAS_STEP_PLAN] one memset of small_dev, bas_plan_build for the
@@ -280,6 +289,11 @@ int bas_render_step(const bas_step_job* job, void* stream);
  * split.  Contents need no initialisation and carry nothing between calls; concurrent bas_render
  * calls (different streams) need a workspace each. */
 long long bas_render_workspace_bytes(void);
+
+/* Diagnostics, off by default: while trace_dev is non-NULL every CTA of the tiled render kernels launched by this
+ * process stores {start ns, end ns, SM id, work items} (4 x u64 per CTA, room for 4 x 148 x 4 CTAs) - where does the
+ * tail of a launch go (tools/cta_trace.py).  Pass NULL to switch it off again. */
+int bas_render_set_trace(unsigned long long* trace_dev);
 
 /* apply_hrtf.py:462-464: divide n floats by *peak_dev when it exceeds 1 (no-op otherwise). */
 int bas_normalise(float* out_dev, long long n, const float* peak_dev, void* stream);

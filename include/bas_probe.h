@@ -38,6 +38,9 @@ int bas_probe_block(int ctas_per_sm, int blocks, int iters, float* sink_dev, voi
 int bas_probe_tc_render(const float* x_dev, long long n_in, const float* filt_dev, int K, int C, float* out_dev,
                         long long out_stride, long long n_out, int mode, int blocks, float* sink_dev, void* stream);
 
+/* One-thread kernel that stores %globaltimer (ns) into *slot_dev: a time stamp in stream order. */
+int bas_probe_stamp(unsigned long long* slot_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -255,3 +255,35 @@ def test_chunk_sizes_the_fused_kernel_cannot_stage_fall_back_up_front(bas, oracl
     mix = bas.render_sources(xd, chunk, sub, [_traj(3), _traj(3)], synth_bank, mix=True, normalise=False, return_device=True).cpu().numpy()
     want_n_in = oracle.make_signal_move_2d(np.concatenate([x, np.zeros(n_in - x.size, dtype=np.float32)]), chunk, sub, _traj(3), synth_bank)
     close(mix.T, 2.0 * want_n_in)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('n_src,seconds,fused', [(8, 20, True), (3, 30, True), (5, 12, False)])
+def test_long_mix_of_few_sources_peaks_and_second_pass(bas, synth_bank, n_src, seconds, fused, monkeypatch):
+    """Long mixes with few sources: every tile of the mixing kernel is shared by two CTAs (stream-K spans of 17 - 70
+    (tile, source) slices, partial sums through the workspace).  The mix must be the sum of the sources, every per-source
+    peak the peak of the complete source (apply_hrtf.py:462), and the second (normalising) pass must use it."""
+    import torch
+    ah = bas.apply_hrtf
+    ah.PROGRESS = False
+    monkeypatch.setattr(ah, 'FUSED', 'auto' if fused else False)
+    rng = np.random.default_rng(77 + n_src)
+    n = seconds * 44100
+    x = (0.02 * rng.standard_normal((n_src, n))).astype(np.float32)
+    loud = n_src // 2
+    x[loud] *= 30.0                                          # peaks above 1: normalised on its own in the second pass
+    trajs = [(lambda t, s=s: (0.6 * np.sin(2e-5 * t + s), (3e-5 * t + 0.7 * s) % (2 * np.pi))) for s in range(n_src)]
+    xd = torch.from_numpy(x).cuda()
+    each, peaks_each = ah.render_sources(xd, 512, 32, trajs, synth_bank, mix=False, normalise=False, return_device=True, return_peaks=True)
+    mix, peaks_mix = ah.render_sources(xd, 512, 32, trajs, synth_bank, mix=True, normalise=False, return_device=True, return_peaks=True)
+    want = each.double().sum(dim=0)
+    assert float((mix.double() - want).norm() / want.norm()) <= 1e-6
+    assert np.allclose(peaks_mix, peaks_each, rtol=2e-6, atol=0) and peaks_mix[loud] > 1
+    normed = ah.render_sources(xd, 512, 32, trajs, synth_bank, mix=True, return_device=True)
+    gains = torch.ones(n_src, dtype=torch.float64, device='cuda')
+    gains[loud] = 1.0 / float(peaks_each[loud])
+    want_n = (each.double() * gains[:, None, None]).sum(dim=0)
+    assert float((normed.double() - want_n).norm() / want_n.norm()) <= 1e-6
+    # the same launch twice: identical bits (fixed order of summation, also across the CTA boundary)
+    again = ah.render_sources(xd, 512, 32, trajs, synth_bank, mix=True, normalise=False, return_device=True)
+    assert torch.equal(again, mix)

@@ -33,7 +33,7 @@ def test_header_symbols_exported(bas):
     for name in declared:
         assert hasattr(lib, name), name
     assert declared == set(bas._cabi.EXPORTS)
-    assert lib.bas_abi_version() == bas._cabi.ABI_VERSION == 4
+    assert lib.bas_abi_version() == bas._cabi.ABI_VERSION == 5
 
 
 def test_probe_library_is_separate(bas):

@@ -56,6 +56,51 @@ if rank == 0:
         got = out_dst
     out['by_source_sourceless_rank_rel_l2'] = rel(got, ref_few.astype(np.float64))
 
+# ---- a stream of batches, the exchange of a batch beside the render of the next (PeerMix pipelined) ----
+n_b = 4 * 44100
+batches, refs = [], []
+for b in range(5):
+    sb = np.stack([bench.pink_noise(n_b, 900 + 10 * b + s) for s in range(2 * world)])
+    tb = [bench.lissajous(7 * b + s) for s in range(2 * world)]
+    mine_b = bas.distributed.shard_sources(2 * world, rank, world)
+    batches.append((torch.from_numpy(sb[mine_b]).cuda(), [tb[s] for s in mine_b]))
+    if rank == 0:
+        refs.append(bas.render_sources(sb, 512, 32, tb, bank, mix=True, normalise=False).astype(np.float64))
+for replicate in (True, False):
+    worst, same = 0.0, True
+    for b, got in enumerate(bas.distributed.render_mix_stream(batches, 512, 32, bank, replicate=replicate)):
+        got = got.clone()
+        if replicate:
+            every = [None] * world
+            dist.all_gather_object(every, float(got.double().abs().sum()))
+            same = same and max(every) == min(every)
+            if rank == 0:
+                worst = max(worst, rel(got.cpu().numpy(), refs[b]))
+        else:
+            peer = bas.distributed._peer_mix(got.shape[1], None) if world > 1 else None
+            lo, cnt = peer.slice if peer is not None else (0, got.shape[1])
+            piece = torch.zeros((2, peer.slice_len if peer is not None else got.shape[1]), dtype=torch.float32, device='cuda')
+            piece[:, :cnt] = got[:, lo:lo + cnt]
+            pieces = [torch.empty_like(piece) for _ in range(world)]
+            dist.all_gather(pieces, piece)
+            full = torch.cat(pieces, dim=1)[:, :got.shape[1]]
+            if rank == 0:
+                worst = max(worst, rel(full.cpu().numpy(), refs[b]))
+    if rank == 0:
+        out['stream_%s_rel_l2_vs_one_gpu' % ('replicated' if replicate else 'sharded')] = worst
+        if replicate:
+            out['stream_same_on_every_rank'] = bool(same)
+# a failing trajectory on the LAST rank only raises everywhere
+bad = [(batches[0][0], [(lambda t: (0.0, float('nan')))] * len(batches[0][1]) if rank == world - 1 else batches[0][1])]
+try:
+    list(bas.distributed.render_mix_stream(bad, 512, 32, bank))
+    raised = False
+except (ValueError, AssertionError, bas.BasError):
+    raised = True
+every = [None] * world
+dist.all_gather_object(every, raised)
+out['stream_error_raises_on_every_rank'] = bool(all(every))
+
 # ---- by time (config 4) ----
 x = 30.0 * bench.pink_noise(20 * 44100 + 123, 7)   # peaks above 1: exercises the global normalisation
 traj = bench.lissajous(3)
@@ -66,7 +111,8 @@ if rank == 0:
     out['by_time_peak'] = float(np.abs(full).max())
     out['by_time_shape'] = list(full.shape)
     ok = (out['by_source_peer_rel_l2_vs_one_gpu'] < 1e-6 and out['by_source_nccl_rel_l2_vs_one_gpu'] < 1e-6 and out['by_source_peer_same_on_every_rank'] and
-          out['by_source_sourceless_rank_rel_l2'] < 1e-6 and out['by_time_rel_l2_vs_one_gpu'] < 1e-6 and abs(out['by_time_peak'] - 1) < 1e-6)
+          out['by_source_sourceless_rank_rel_l2'] < 1e-6 and out['stream_replicated_rel_l2_vs_one_gpu'] < 1e-6 and
+          out['stream_sharded_rel_l2_vs_one_gpu'] < 1e-6 and out['stream_same_on_every_rank'] and out['stream_error_raises_on_every_rank'] and out['by_time_rel_l2_vs_one_gpu'] < 1e-6 and abs(out['by_time_peak'] - 1) < 1e-6)
     out['world'] = world
     out['ok'] = bool(ok)
     print(json.dumps(out))

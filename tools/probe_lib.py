@@ -11,7 +11,7 @@ def load():
     lib = C.CDLL(LIB_PATH)
     vp, i = C.c_void_p, C.c_int
     for name, argtypes in {'bas_probe_clock': [i, i, i, i, vp, vp, vp], 'bas_probe_block': [i, i, i, vp, vp],
-                           'bas_probe_fma': [i, i, i, i, vp, vp],
+                           'bas_probe_fma': [i, i, i, i, vp, vp], 'bas_probe_stamp': [vp, vp],
                            'bas_probe_tc_render': [vp, C.c_longlong, vp, i, i, vp, C.c_longlong, C.c_longlong, i, i, vp, vp]}.items():
         fn = getattr(lib, name)
         fn.argtypes, fn.restype = argtypes, i
