@@ -8,10 +8,12 @@ Under torchrun (N > 1) one rank per GPU over NCCL.  --config selects the workloa
   mix64 (default)  BASELINE.json configs[2]: 64 independent 60 s sources, each on its own Lissajous
                    trajectory, mixed to ONE binaural output; sources sharded round-robin over the
                    ranks (strong scaling: the job is the same at every N) and the per-rank mixes
-                   summed INSIDE the timed step: fused with the render kernel over NVLink peer memory
-                   (--collective peer_sharded, the default: summed mix left sharded by time; peer:
-                   replicated on every rank) or by NCCL (all_reduce / reduce, optionally per time segment).
-                   A step = plan (64 x 5169 directions) + render/mix + exchange.
+                   summed INSIDE the timed region: fused with the render kernel over NVLink peer memory
+                   (--collective peer_pipelined, the default: the exchange of a step runs beside the plan
+                   and render of the next, the timed region ends when the last exchange is complete
+                   everywhere, summed mix left sharded by time; peer_sharded: the exchange inside its own
+                   step; peer: replicated on every rank) or by NCCL (all_reduce / reduce, optionally per
+                   time segment).  A step = plan (64 x 5169 directions) + render/mix + exchange.
   single           configs[1]: one 60 s source per rank (weak scaling, no collective).
   hour             configs[3]: one 1-hour 48 kHz source cut across the ranks by time (K-1 halo),
                    global peak by MAX all-reduce.
