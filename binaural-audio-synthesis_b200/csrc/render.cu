@@ -217,7 +217,10 @@ static int render_common(const float* x_dev, long long x_stride, long long n_val
                     const double slots = (double)device_sm_count() * ctas;
                     const double blocks_per_tile = (double)((D + parts - 1) / parts) * (prm.mix ? n_src : 1);
                     double waves = tiles / slots;
-                    if (!(can_split && waves > 1.0)) {
+                    // mixing with a workspace: a tile's sources may be dealt to a chain of CTAs (render_tiled.cuh), so
+                    // fewer tiles than CTAs still fill the device
+                    const bool chain = prm.mix && can_split && tiles * n_src / slots >= (double)((n_src + 7) / 8 + 1);
+                    if (!(can_split && (waves > 1.0 || chain))) {
                         // whole tiles, dealt round-robin; the last wave only occupies part of every SM and
                         // its CTAs then run with fewer neighbours on the FMA pipe
                         const double full = (double)(long long)waves, rest = waves - full;

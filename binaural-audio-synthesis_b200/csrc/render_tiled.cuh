@@ -287,6 +287,13 @@ __device__ __forceinline__ void block_diag(u64 (&acc)[kBlk], const float2* __res
 // else, so the wait cannot deadlock even when not all CTAs are resident at once.  Every scheduler
 // gets the same number of 32x32 blocks and results stay deterministic.  Without a workspace spans
 // are rounded to group boundaries.
+// CHAIN kernels (mixing only): a launch with fewer tiles than CTAs (a time range of a long mix: 39 tiles x 64 sources)
+// still fills the device - spans may be SHORTER than a group, down to 1 / kMaxChain of it.  A CTA in the middle of a
+// tile runs its sources, waits for its successor's partial sums, adds them to its own and publishes the total to its
+// predecessor: the sums of a tile travel down a chain of at most kMaxChain + 1 CTAs (all resident: the grid is never
+// larger than what the device holds), later sources first, in a fixed order.  A kernel instance of its own, so that
+// the code of the common case stays what it was.
+constexpr int kMaxChain = 8;
 struct SpanInfo { long long total, n_groups; int gs; int split; unsigned long long epoch; };
 
 __host__ __device__ inline long long span_begin(const SpanInfo& sp, long long c, long long G) {
@@ -300,6 +307,7 @@ struct Item {
     bool group_end;         // outputs of the group are complete (for this CTA) after this item
     bool partial;           // this CTA holds only part of the group -> workspace
     int slot;               // workspace slot: 0 = group began in the previous CTA, 1 = continues in the next
+    bool goes_on;           // CHAIN: the group continues in the next CTA (also when it began in an earlier one)
 };
 
 __device__ __forceinline__ void flag_release(unsigned long long* flag, unsigned long long v) {
@@ -340,7 +348,7 @@ __device__ __forceinline__ void cta_barrier(int threads) {
 // producers also issue the TMA copies of the input rows.  Same terms, same order of summation: the rows
 // are bit-identical to bas_ir_synth's.
 // SUBS: subchunks per 32-sample row (see block_diag): 1 for subchunksize 32, 64, 96, ...; 2 for subchunksize 16.
-template <int TW, bool MIX, int NS, int MINB, bool FUSED = false, int SUBS = 1>
+template <int TW, bool MIX, int NS, int MINB, bool FUSED = false, int SUBS = 1, bool CHAIN = false>
 __global__ void __launch_bounds__((FUSED ? 2 * TW : TW) * 32, MINB)
 bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ workspace, const __grid_constant__ CUtensorMap xmap) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -427,6 +435,7 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
         }
         it.partial = a > 0 || b < sp.gs;
         it.slot = a > 0 ? 0 : 1;
+        it.goes_on = b < sp.gs;
         if (MIX) {
             it.tile = grp;
             it.d0 = 0; it.d1 = g.D;
@@ -751,6 +760,14 @@ bas_render_tiled_kernel(RenderParams prm, SpanInfo sp, float* __restrict__ works
                 if (warp_live) {
                     const long long slot = (long long)blockIdx.x * TS + stripe;
                     u64* dstp = ws_sums + slot * kWarpTile + lane;
+                    if (CHAIN && it.goes_on) {                  // middle of a chain: own sources + everything after them
+                        const long long next = (long long)(blockIdx.x + 1) * TS + stripe;
+                        if (lane == 0) flag_wait(ws_flags + next, sp.epoch);
+                        __syncwarp();
+                        const u64* srcp = ws_sums + next * kWarpTile + lane;
+#pragma unroll
+                        for (int r = 0; r < kBlk; ++r) acc[r] = add2(acc[r], __ldcg(srcp + r * 32));
+                    }
 #pragma unroll
                     for (int r = 0; r < kBlk; ++r) __stcg(dstp + r * 32, acc[r]);
                     __threadfence();
@@ -881,7 +898,8 @@ int launch_tiled(RenderParams prm, int parts, bool want_split, float* workspace,
     size_t smem = tile_smem_bytes(g, TW, NS, parts, prm.C, MIX, prm.tmap != 0, FUSED, prm.nf);
     if (FUSED && smem > 227 * 1024) { prm.nf = 1; smem = tile_smem_bytes(g, TW, NS, parts, prm.C, MIX, prm.tmap != 0, FUSED, 1); }
     if (smem > 227 * 1024) return BAS_E_UNSUPPORTED;
-    auto kern = bas_render_tiled_kernel<TW, MIX, NS, MINB, FUSED, SUBS>;
+    using Kernel = void (*)(RenderParams, SpanInfo, float*, const CUtensorMap);
+    Kernel kern = bas_render_tiled_kernel<TW, MIX, NS, MINB, FUSED, SUBS, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { bas_set_error("bas_render: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     const long long p_base = prm.p_begin / kBlk * kBlk;
@@ -899,12 +917,25 @@ int launch_tiled(RenderParams prm, int parts, bool want_split, float* workspace,
     int per_sm = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem);
     if (e != cudaSuccess || per_sm < 1) { bas_set_error("bas_render: tile shape does not fit an SM"); cudaGetLastError(); return BAS_E_UNSUPPORTED; }
-    long long grid = (long long)device_sm_count() * per_sm;
+    const long long resident = (long long)device_sm_count() * per_sm;
+    long long grid = resident;
     if (grid > sp.n_groups) grid = sp.n_groups;
     // split groups between CTAs only when every span is longer than a group (then a group has at
     // most two contributors) and the caller gave a workspace
     const long long need = (long long)ws_bytes(grid, TS);
     sp.split = (want_split && workspace && workspace_bytes >= need && grid > 1 && sp.total / grid >= sp.gs + 1) ? 1 : 0;
+    if constexpr (MIX) {
+        // fewer tiles than the device holds CTAs: the CHAIN kernel, spans of at least 1 / kMaxChain of a tile's sources
+        const long long min_span = (sp.gs + kMaxChain - 1) / kMaxChain + 1;
+        long long grid_chain = resident < sp.total / min_span ? resident : sp.total / min_span;
+        if (!sp.split && want_split && workspace && grid_chain > grid && workspace_bytes >= (long long)ws_bytes(grid_chain, TS)) {
+            kern = bas_render_tiled_kernel<TW, MIX, NS, MINB, FUSED, SUBS, true>;
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) { bas_set_error("bas_render: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+            grid = grid_chain;
+            sp.split = 1;
+        }
+    }
     sp.epoch = sp.split ? next_epoch() : 0ull;
     e = bas_launch(kern, dim3((unsigned)grid), dim3(kThreads), smem, st, prm, sp, workspace, xmap);
     if (e != cudaSuccess) { bas_set_error("bas_render: tiled launch failed: %s", cudaGetErrorString(e)); return (int)e; }

@@ -258,11 +258,12 @@ def test_chunk_sizes_the_fused_kernel_cannot_stage_fall_back_up_front(bas, oracl
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('n_src,seconds,fused', [(8, 20, True), (3, 30, True), (5, 12, False)])
+@pytest.mark.parametrize('n_src,seconds,fused', [(8, 20, True), (3, 30, True), (5, 12, False), (48, 3, True), (20, 1, False)])
 def test_long_mix_of_few_sources_peaks_and_second_pass(bas, synth_bank, n_src, seconds, fused, monkeypatch):
     """Long mixes with few sources: every tile of the mixing kernel is shared by two CTAs (stream-K spans of 17 - 70
-    (tile, source) slices, partial sums through the workspace).  The mix must be the sum of the sources, every per-source
-    peak the peak of the complete source (apply_hrtf.py:462), and the second (normalising) pass must use it."""
+    (tile, source) slices, partial sums through the workspace); short mixes of many sources: fewer tiles than CTAs, the
+    sums of a tile travel down a chain of CTAs.  The mix must be the sum of the sources, every per-source peak the
+    peak of the complete source (apply_hrtf.py:462), and the second (normalising) pass must use it."""
     import torch
     ah = bas.apply_hrtf
     ah.PROGRESS = False

@@ -18,13 +18,14 @@ stride = (n_out + 3) // 4 * 4
 times = np.arange(0, n_in + 1, 512, dtype=np.int64)
 st = torch.cuda.current_stream().cuda_stream
 trace = torch.zeros(4 * 148 * 4 * 4, dtype=torch.int64, device=dev)
+variant = int(os.environ.get('BAS_TRACE_VARIANT', '0'), 0)          # a bas_render variant word (cabi.render_variant), 0: the library's choice
 for n_src in [int(a) for a in sys.argv[1:]] or [64, 8, 1]:
     mix = n_src > 1
     x = torch.randn((n_src, n_in), device=dev) * 0.01
     dirs = [bench.lissajous(s)(times) for s in range(n_src)]
     elev = torch.from_numpy(np.stack([d[0] for d in dirs])).to(dev)
     azim = torch.from_numpy(np.stack([d[1] for d in dirs])).to(dev)
-    job = ah.DeviceRender(torch, bdev, x, n_in, 512, 32, elev.reshape(-1), azim.reshape(-1), cabi.AZ_F64, mix, 0)
+    job = ah.DeviceRender(torch, bdev, x, n_in, 512, 32, elev.reshape(-1), azim.reshape(-1), cabi.AZ_F64, mix, variant)
     out = torch.zeros((2, stride) if mix else (1, 2, stride), dtype=torch.float32, device=dev)
     job.plan(st)
     for rep in range(3):
@@ -47,7 +48,7 @@ for n_src in [int(a) for a in sys.argv[1:]] or [64, 8, 1]:
                      'duration_us_min_median_max': [round(float(v), 1) for v in np.percentile(dur, [0, 50, 100])],
                      'idle_tail_mean_us': round(float((end.max() - end).mean()), 1), 'items_min_max': [int(items.min()), int(items.max())]})
     order = np.argsort(end)
-    print(json.dumps({'n_src': n_src, 'launches': rows,
+    print(json.dumps({'n_src': n_src, 'variant': hex(variant), 'launches': rows,
                       'earliest_10': [[int(smid[i]), round(float(end[i]), 1), int(items[i])] for i in order[:10]],
                       'latest_10': [[int(smid[i]), round(float(end[i]), 1), int(items[i])] for i in order[-10:]],
                       'end_by_sm_mod_2': [round(float(end[smid % 2 == p].mean()), 1) for p in (0, 1)],

@@ -58,3 +58,28 @@ for _ in range(3):
     bas.render_sources(x_page, 512, 32, plain, bank, mix=True)
 pr.disable()
 s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats('cumulative').print_stats(14); print(s.getvalue()[:3000])
+
+# the same time ranges rendered from device-resident input, back to back (GPU busy, no copies in flight): is a phase's
+# render slower inside the pipeline than on its own?
+import subprocess
+xd = torch.from_numpy(x).cuda()
+k, n_in, n_out = bas.render_geometry(n, 512, 32, bank)
+cuts = [0, 212992, 532480, 933888, 1327104, 1720320, 2121728, 2441216, n_out]
+times = np.arange(0, n_in + 1, 512, dtype=np.int64)
+dirs = [bench.lissajous(s)(times) for s in range(n_src)]
+pre = (np.stack([d_[0] for d_ in dirs]), np.stack([d_[1] for d_ in dirs]), bas._cabi.AZ_F64)
+pre_d = (torch.from_numpy(pre[0]).cuda(), torch.from_numpy(pre[1]).cuda(), pre[2])
+for rep in range(2):
+    row = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        if rep == 1:
+            time.sleep(0.02)                                 # let the GPU go idle first, like between the phases of a call
+        e0.record()
+        bas.render_sources(xd, 512, 32, pre_d, bank, mix=True, normalise=False, return_device=True, time_range=(a, b))
+        e1.record(); torch.cuda.synchronize()
+        row.append(round(e0.elapsed_time(e1) * 1e3))
+    print('device-resident ranges (plan of all points + render), us, %s: %s' % ('after 20 ms idle' if rep else 'back to back', row))
+q = subprocess.run(['nvidia-smi', '--query-gpu=clocks.sm,clocks.mem,pstate,power.draw', '--format=csv,noheader'], capture_output=True, text=True)
+print('idle now:', q.stdout.strip())
