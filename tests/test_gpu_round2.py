@@ -288,3 +288,36 @@ def test_long_mix_of_few_sources_peaks_and_second_pass(bas, synth_bank, n_src, s
     # the same launch twice: identical bits (fixed order of summation, also across the CTA boundary)
     again = ah.render_sources(xd, 512, 32, trajs, synth_bank, mix=True, normalise=False, return_device=True)
     assert torch.equal(again, mix)
+
+
+@pytest.mark.gpu
+def test_render_mix_stream_on_one_rank(bas, synth_bank):
+    """distributed.render_mix_stream with a one-rank group: every batch comes out, in order, equal to render_sources'
+    mix of the same sources; a failing trajectory raises when its batch is collected.  (The multi-rank exchange is
+    checked on real GPUs by tools/dist_check.py and by bench.py's parity field.)"""
+    import torch
+    import torch.distributed as dist
+    ah = bas.apply_hrtf
+    ah.PROGRESS = False
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group('nccl', init_method='tcp://127.0.0.1:29571', rank=0, world_size=1, device_id=torch.device('cuda', 0))
+    try:
+        rng = np.random.default_rng(5)
+        n = 3 * 44100
+        batches, want = [], []
+        for b in range(4):
+            x = torch.from_numpy((0.02 * rng.standard_normal((3, n))).astype(np.float32)).cuda()
+            trajs = [(lambda t, s=s, b=b: (0.5 * np.sin(3e-5 * t + s + b), (4e-5 * t + s) % (2 * np.pi))) for s in range(3)]
+            batches.append((x, trajs))
+            want.append(ah.render_sources(x, 512, 32, trajs, synth_bank, mix=True, normalise=False, return_device=True).clone())
+        got = [g.clone() for g in bas.distributed.render_mix_stream(batches, 512, 32, synth_bank)]
+        assert len(got) == 4
+        for g, w in zip(got, want):
+            assert torch.equal(g, w)
+        bad = [(batches[0][0], [lambda t: (0.0, float('nan'))] * 3)]
+        with pytest.raises(AssertionError):                  # a NaN azimuth fails the reference's `assert azim >= 0` first (sphere.py:87)
+            list(bas.distributed.render_mix_stream(bad, 512, 32, synth_bank))
+    finally:
+        if created:
+            dist.destroy_process_group()
