@@ -762,7 +762,10 @@ def _render_pipeline(torch, dev, src, chunksize, subchunksize, elev_azim_functio
         # signal upload (the long pole) runs anyway.  Two evaluations per trajectory instead: the stretch the first
         # phase needs - so that rendering starts early - and all the rest while that phase uploads and renders;
         # one plan launch each.
-        pt_a = phases[0][3]
+        # Dozens of sources: the upload alone takes longer than everything the device has to do, so nothing is gained by
+        # starting the first phase early - but the host must be through with all trajectories well before the last
+        # sample has arrived.  ONE evaluation per trajectory (all points; one plan launch), with fewer spot checks.
+        pt_a = phases[0][3] if n_src < 16 else n_pts
         phases = [(pa, pb, 0, pt_a) if i == 0 else (pa, pb, pt_a, n_pts) if i == 1 else (pa, pb, n_pts, n_pts)
                   for i, (pa, pb, _, _) in enumerate(phases)]
         if n_src >= 16:
