@@ -228,7 +228,11 @@ static int render_common(const float* x_dev, long long x_stride, long long n_val
                     }
                     const int wps = (ctas * sh.tw + 3) / 4;
                     double cost = waves * blocks_per_tile * wps;
-                    cost *= 1.0 + 0.25 * (parts - 1) + (sh.ns == 1 && ctas == 1 ? 0.02 : 0.0) + (wps < 2 ? 0.3 : 0.0) +
+                    // fused: with room for ONE filter-row buffer only (long filters: K = 512 rows of an 8-stripe tile) the
+                    // producers cannot run an item ahead - measured 141 us per source against 131 us for the same CTA with
+                    // two warps per stripe (half the tile, two buffers; tools/mix_bench.py 32 512 16)
+                    const bool one_buffer = fused && tile_smem_bytes(tile_geom(K, C, prm.pitch, ts), sh.tw, sh.ns, parts, C, prm.mix != 0, use_tmap, true, 2) > 227 * 1024;
+                    cost *= 1.0 + 0.25 * (parts - 1) + (sh.ns == 1 && ctas == 1 ? 0.02 : 0.0) + (wps < 2 ? 0.3 : 0.0) + (one_buffer ? 0.30 : 0.0) +
                             (prm.mix ? (sh.tw == 8 ? -0.05 : sh.minb == 3 ? 0.03 : 0.0) : (sh.tw == 4 ? 0.0 : 0.05));
                     if (!best || cost < best_cost) { best = &sh; best_parts = parts; best_cost = cost; }
                 }
