@@ -652,7 +652,10 @@ def run_mix(ctx, name):
             assert not mix_mode or float(small[2:].view(np.float32).max()) <= 1.0
     per_rank = ctx.gather_objects({'rank': rank, 'mean_ms': float(np.mean(per_step)), 'min_ms': float(np.min(per_step)),
                                    'median_ms': float(np.median(per_step)), 'max_ms': float(np.max(per_step)), 'sources': n_local})
-    launches_per_step = ((1 + len(segs)) if n_local else 0) + (2 if peer is not None else 0)     # plan_build + renders (+ peer kernels)
+    # plan_build + renders, + the peer kernels: pipelined = the reduce (its waits are stream memory operations, or two
+    # wait kernels where the driver has none); inside the step = wait + reduce
+    peer_kernels = 0 if peer is None else (1 if peer._stream_wait_ok else 3) if pipelined else 2
+    launches_per_step = ((1 + len(segs)) if n_local else 0) + peer_kernels
     if not mix_mode:
         launches_per_step += n_local
 
@@ -680,7 +683,8 @@ def run_mix(ctx, name):
                    'value_counts': 'source-sample-pairs/s: every source contributes N_out = %d output pairs per step' % n_out,
                    'l2_policy': 'steps rotate over %d input/output set(s) of %.0f MB per rank (L2: 126 MB)' % (n_sets, set_bytes / 1e6),
                    'kernels_per_step': 'memset, plan_build, %d x render (filter rows synthesised by producer warps in-kernel)%s' % (
-                       len(segs), ', peer_reduce (+ peer_wait)' if peer is not None else
+                       len(segs), (', peer_reduce on a side stream (waits for the peers: cuStreamWaitValue32)' if pipelined and peer._stream_wait_ok else
+                                   ', peer_reduce (+ peer_wait)') if peer is not None else
                        ', 2 x %d NCCL %s' % (len(segs), collective) if collective != 'none' else '')},
         'clocks': clocks.summary(), 'gpu_launches': launches_per_step * args.steps,
         'per_rank_step_ms': {'min_of_means': min(p['mean_ms'] for p in per_rank), 'median_of_means': float(np.median([p['mean_ms'] for p in per_rank])),
